@@ -1,0 +1,280 @@
+/* visfd_cuda.h -- C ABI of the B200 (sm_100a) implementation of visfd's
+ * filter_mrc membrane / blob hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.
+ * Every entry point names the reference interface it replaces (paths are into
+ * the jewettaij/visfd tree).  The C++ mirror of the reference's `namespace visfd`
+ * template API that forwards to these symbols is visfd_b200/csrc/visfd_cuda_shim.hpp;
+ * INTEGRATION.md shows the reference-side patch.
+ *
+ * Conventions
+ *  - Volumes are dense row-major float32 [nz][ny][nx] (x fastest), exactly the
+ *    contiguous block behind Alloc3D<float> (lib/visfd/alloc3d.hpp:25-67).
+ *  - Vector fields are AoS float[N][3] (array<float,3>***), tensors AoS
+ *    float[N][6] in flat order xx,yy,zz,xy,yz,xz (lib/visfd/lin3_utils.hpp:400-406).
+ *  - Masks are float volumes: 0 = ignore, anything else = weight
+ *    (lib/visfd/filter1d.hpp:273-275).  NULL = no mask.
+ *  - Every array argument may be a HOST pointer (the library stages it through
+ *    device memory: this is the drop-in path) or a DEVICE pointer on the
+ *    context's GPU (no copies: the resident path used by the multi-GPU driver
+ *    and the benchmark).  All arrays of one call must be of the same kind.
+ *  - All sizes are 64-bit; the reference's `int` limits (alloc3d.hpp:33-35,
+ *    multichannel_image3d.hpp:126-133) do not apply.
+ *  - Calls are synchronous (results are complete on return) and return 0 on
+ *    success, non-zero on failure with a message in visfd_cuda_last_error().
+ *    The C++ shim rethrows it as VisfdErr (lib/visfd/err_visfd.hpp:15-22).
+ *  - There is no CPU fallback: without a usable CUDA device every call fails.
+ *
+ * Z-slab form.  Entry points ending in _slab operate on a slab of nz_local
+ * planes that represents global planes [z_offset, z_offset+nz_local) of a volume
+ * with nz_global planes: image-border behaviour (zero extension + renormalisation,
+ * clamped finite-difference stencils) is applied at the GLOBAL borders only, so a
+ * slab carrying a halo of at least the stencil radius reproduces the single-volume
+ * result on its interior planes.  The non-slab forms are the slab forms with
+ * z_offset = 0 and nz_global = nz.
+ */
+#ifndef VISFD_CUDA_H
+#define VISFD_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct visfd_ctx visfd_ctx;
+
+#define VISFD_INCREASING_EIVALS 0 /* selfadjoint_eigen3::INCREASING_EIVALS, eigen3_simple.hpp:36-43 */
+#define VISFD_DECREASING_EIVALS 1 /* selfadjoint_eigen3::DECREASING_EIVALS */
+
+#define VISFD_SCORE_PLANAR 0 /* ScoreHessianPlanar / ScoreTensorPlanar, feature.hpp:1529, 1593 */
+#define VISFD_SCORE_LINEAR 1 /* ScoreHessianLinear / ScoreTensorLinear, feature.hpp:1572, 1610 */
+
+/* ---- context -------------------------------------------------------------- */
+int visfd_cuda_version(void);
+/* One context per GPU.  device < 0 selects the current device. */
+int visfd_cuda_init(int device, visfd_ctx **ctx);
+void visfd_cuda_destroy(visfd_ctx *ctx);
+const char *visfd_cuda_last_error(void);
+/* Use an existing stream (cudaStream_t passed as void*) for all work of ctx. */
+int visfd_cuda_set_stream(visfd_ctx *ctx, void *cuda_stream);
+/* Release cached device workspace. */
+int visfd_cuda_trim(visfd_ctx *ctx);
+/* Number of kernel launches issued by ctx since creation (bench bookkeeping). */
+int64_t visfd_cuda_launch_count(visfd_ctx *ctx);
+/* Device milliseconds the most recent call spent in its named stage, measured
+ * with CUDA events on the context's stream: "gauss", "ridge", "select", "compact",
+ * "tv", "threshold", "h2d", "d2h".  Returns -1 for an unknown stage. */
+double visfd_cuda_stage_ms(visfd_ctx *ctx, const char *stage);
+
+/* ---- host-side parameter helpers (no GPU work) ----------------------------- */
+/* GenFilterGauss1D<float>(sigma, halfwidth): lib/visfd/filter1d.hpp:411-460.
+ * taps[i+hw], i = -hw..hw. */
+void visfd_cuda_gen_gauss1d(float sigma, int hw, float *taps);
+/* Halfwidth rules: max(1,floor(sigma*ratio)) (lib/visfd/filter3d.hpp:1241-1246);
+ * ratio <= 0 means ratio = sqrt(-2 ln threshold)
+ * (bin/filter_mrc/filter3d_variants.hpp:500-528). */
+int visfd_cuda_gauss_halfwidth(float sigma, float truncate_ratio, float truncate_threshold);
+/* TV3D::SetSigma: hw = floor(sigma*cutoff_ratio), lib/visfd/feature.hpp:1669-1675 */
+int visfd_cuda_tv_halfwidth(float sigma, float cutoff_ratio);
+
+/* ---- separable filters ----------------------------------------------------- */
+/* ApplySeparable<float>: lib/visfd/filter3d.hpp:688-1050.
+ * taps[d] -> 2*hw[d]+1 floats (host memory), d = 0:x 1:y 2:z.  *A_out (may be
+ * NULL) receives the returned peak height. */
+int visfd_cuda_apply_separable(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                               const float *src, float *dst, const float *mask,
+                               const float *const taps[3], const int hw[3],
+                               int normalize, float *A_out);
+/* ApplyGauss<float>(sigma[3], truncate_halfwidth[3]): lib/visfd/filter3d.hpp:1088-1124
+ * (the other three overloads, :1163, :1228, :1299, and the filter_mrc variant,
+ * filter3d_variants.hpp:500-528, are argument adapters over this one). */
+int visfd_cuda_apply_gauss(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                           const float *src, float *dst, const float *mask,
+                           const float sigma[3], const int hw[3], int normalize,
+                           float *A_out);
+int visfd_cuda_apply_gauss_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local,
+                                int64_t z_offset, int64_t nz_global, const float *src,
+                                float *dst, const float *mask, const float sigma[3],
+                                const int hw[3], int normalize, float *A_out);
+/* ApplyDog<float>: lib/visfd/filter3d.hpp:1340-1402 */
+int visfd_cuda_apply_dog(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                         const float *src, float *dst, const float *mask,
+                         const float sigma_a[3], const float sigma_b[3], const int hw[3],
+                         float *A_out, float *B_out);
+/* ApplyLog<float>: lib/visfd/filter3d.hpp:1430-1507 */
+int visfd_cuda_apply_log(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                         const float *src, float *dst, const float *mask,
+                         const float sigma[3], float delta_sigma_over_sigma,
+                         float truncate_ratio, float *A_out, float *B_out);
+int visfd_cuda_apply_log_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local,
+                              int64_t z_offset, int64_t nz_global, const float *src,
+                              float *dst, const float *mask, const float sigma[3],
+                              float delta_sigma_over_sigma, float truncate_ratio,
+                              float *A_out, float *B_out);
+
+/* ---- Hessian, eigensolve, ridge saliency ------------------------------------ */
+/* CalcHessian<float, array<float,3>, float*>: lib/visfd/feature.hpp:1210-1348.
+ * gradient (N*3) and hessian (N*6) may each be NULL.  Entries of voxels whose
+ * mask is 0 are left untouched. */
+int visfd_cuda_calc_hessian(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                            const float *src, const float *mask, float sigma,
+                            float truncate_ratio, float *gradient, float *hessian);
+/* The per-voxel loop of HandleTV, bin/filter_mrc/handlers.cpp:1645-1746, fused
+ * with CalcHessian: smooth, finite-difference Hessian, ConvertFlatSym2Evects3
+ * (lib/visfd/eigen3_simple.hpp:392) and ScoreHessianPlanar/Linear, without
+ * writing the 6-component tensor.  saliency: N floats (0 where mask==0);
+ * direction: N*3 floats = eivects[0] (may be NULL; untouched where mask==0). */
+int visfd_cuda_hessian_ridge(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                             const float *src, const float *mask, float sigma,
+                             float truncate_ratio, int eival_order, int score_kind,
+                             float *saliency, float *direction);
+/* Per-voxel eigen-decomposition + score of an existing N*6 tensor image:
+ * ConvertFlatSym2Evects3 + ScoreHessian* (kind_is_vote_tensor = 0) as in
+ * handlers.cpp:1656-1704, or DiagonalizeFlatSym3 + ScoreTensor* (= 1) as in
+ * handlers.cpp:1870-1892.  eivals (N*3) and direction (N*3) may be NULL.
+ * Voxels with mask==0 keep their previous score. */
+int visfd_cuda_tensor_score(visfd_ctx *ctx, int64_t n_voxels, const float *tensor,
+                            const float *mask, int eival_order, int score_kind,
+                            int kind_is_vote_tensor, float *score, float *eivals,
+                            float *direction);
+
+/* ---- saliency cut ------------------------------------------------------------ */
+/* bin/filter_mrc/handlers.cpp:1751-1797.  is_fraction: threshold = element
+ * floor(n*cut) of the un-masked saliencies sorted in decreasing order; then
+ * every voxel with saliency < threshold is set to 0 in place. */
+int visfd_cuda_saliency_cut(visfd_ctx *ctx, int64_t n_voxels, float *saliency,
+                            const float *mask, float cut, int is_fraction,
+                            float *threshold_out);
+/* Building block of the cut for multi-GPU drivers: 2048-bin histogram of the
+ * order-preserving 32-bit keys of saliency[i] (mask[i]!=0) whose top
+ * `prefix_bits` bits equal `prefix`; bin = next 11 (or the remaining) bits.
+ * hist: 2048 uint64 on the HOST.  Ranks all-reduce hist and call
+ * visfd_cuda_select_step to narrow the prefix. */
+int visfd_cuda_select_hist(visfd_ctx *ctx, int64_t n_voxels, const float *saliency,
+                           const float *mask, uint32_t prefix, int prefix_bits,
+                           uint64_t *hist);
+/* Given a (globally reduced) histogram and the rank still to skip (number of
+ * keys greater than the current prefix range already accounted for), returns
+ * the new prefix/prefix_bits and the updated rank.  Pure host code. */
+int visfd_cuda_select_step(const uint64_t *hist, uint32_t *prefix, int *prefix_bits,
+                           uint64_t *rank);
+/* key <-> float helpers for drivers */
+float visfd_cuda_key_to_float(uint32_t key);
+
+/* ---- tensor voting -------------------------------------------------------------- */
+/* TV3D<float,int,array<float,3>,float*>(sigma, exponent, cutoff_ratio) followed by
+ * TVDenseStick(...): lib/visfd/feature.hpp:1645-1651, 1712-1901, 2218-2384.
+ * tensor: N*6 floats (voxels with mask_dst==0 are left untouched).  normalize and
+ * diagonalize_dest must be 0 (filter_mrc passes false for both,
+ * bin/filter_mrc/handlers.cpp:1834-1835). */
+int visfd_cuda_tv_dense_stick(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                              const float *saliency, const float *direction,
+                              const float *mask_src, const float *mask_dst, float sigma,
+                              int exponent, float cutoff_ratio,
+                              int detect_curves_not_surfaces, int normalize,
+                              int diagonalize_dest, float *tensor);
+
+/* ---- fused membrane pipeline --------------------------------------------------- */
+/* What HandleTV computes between bin/filter_mrc/handlers.cpp:1618 and :1892 when no
+ * background subtraction is requested: CalcHessian -> eigen + planar score ->
+ * saliency cut -> TVDenseStick -> DiagonalizeFlatSym3 + ScoreTensorPlanar.
+ * out: N floats (tomo_out).  Optional outputs (NULL to skip):
+ *   hess_saliency: N floats, ridge saliency after the cut
+ *   direction    : N*3 floats, eivects[0] (only voxels that survive the cut are
+ *                  guaranteed to be filled)
+ *   tensor       : N*6 floats, vote tensor (-save-progress, handlers.cpp:1897-1922)
+ *   threshold_out: the cut threshold used.
+ * tv_sigma <= 0 skips voting (out = saliency after the cut). */
+typedef struct visfd_membrane_params {
+  float sigma;            /* settings.width_a[0] in voxels                       */
+  float truncate_ratio;   /* filter_truncate_ratio (after the threshold rule)    */
+  int eival_order;        /* VISFD_DECREASING_EIVALS for -membrane minima        */
+  float cut;              /* settings.hessian_score_threshold                    */
+  int cut_is_fraction;    /* settings.hessian_score_threshold_is_a_fraction      */
+  float tv_sigma;         /* settings.tv_sigma in voxels                         */
+  int tv_exponent;        /* settings.tv_exponent                                */
+  float tv_cutoff_ratio;  /* settings.tv_truncate_ratio                          */
+} visfd_membrane_params;
+
+int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                        const float *src, const float *mask,
+                        const visfd_membrane_params *p, float *out, float *hess_saliency,
+                        float *direction, float *tensor, float *threshold_out);
+
+/* Slab stages of the same pipeline for the multi-GPU driver (DEVICE pointers only).
+ * A rank owns global planes [z_offset+own_z0, z_offset+own_z1) and holds a slab that
+ * extends them by a halo of RAW SOURCE planes (exchanged once, before stage 1):
+ *   halo >= tv_halfwidth + 1 + gauss_halfwidth   (clipped at the global borders)
+ * so that every later stage is slab-local and the only collective left is the
+ * all-reduce of the cut histograms (visfd_cuda_select_hist / _select_step).
+ * Stage 1: Gaussian + ridge saliency on every plane of the slab; planes closer than
+ *   gauss_halfwidth+1 to an INTERNAL slab face hold incomplete values and must not be
+ *   used (they are exactly the planes outside [vote_z0, vote_z1) below).
+ *   smoothed, saliency: nz_local*ny*nx floats each.
+ * Stage 2 (after the global cut threshold is known): receivers are planes
+ *   [own_z0, own_z1), voters come from planes [vote_z0, vote_z1) (slab-local indices,
+ *   vote range = own range widened by tv_halfwidth, clipped to the volume).
+ *   out: (own_z1-own_z0)*ny*nx floats; tensor (optional): the same region * 6.
+ *   With p->tv_sigma <= 0, out = saliency after the cut. */
+int visfd_cuda_ridge_saliency_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local,
+                                   int64_t z_offset, int64_t nz_global, const float *src,
+                                   const float *mask, float sigma, float truncate_ratio,
+                                   int eival_order, int score_kind, float *smoothed,
+                                   float *saliency);
+int visfd_cuda_vote_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local,
+                         int64_t z_offset, int64_t nz_global, int64_t own_z0, int64_t own_z1,
+                         int64_t vote_z0, int64_t vote_z1, const float *saliency,
+                         const float *smoothed, const float *mask, float threshold,
+                         const visfd_membrane_params *p, float *out, float *tensor);
+
+/* ---- bookkeeping for benchmarks (no reference counterpart) ------------------------- */
+/* Enable/disable the per-stage CUDA-event timing behind visfd_cuda_stage_ms. */
+void visfd_cuda_set_timing(visfd_ctx *ctx, int enabled);
+/* Voters (saliency != 0 after the cut, mask != 0) seen by the most recent voting call. */
+int64_t visfd_cuda_last_voter_count(visfd_ctx *ctx);
+/* Number of (receiver, voter) pairs the reference's TVReceiveStickVotes would evaluate
+ * past its skip tests (feature.hpp:2251-2270) for this input: voters as above, receivers
+ * = in-image voxels with mask_dst != 0 at squared distance <= hw^2.  The roofline's
+ * FLOP count is 35 * pairs.  DEVICE or HOST pointers. */
+int visfd_cuda_tv_count_pairs(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                              const float *saliency, float threshold, const float *mask_src,
+                              const float *mask_dst, int halfwidth, int64_t *pairs);
+/* Sustained FP32 FMA throughput of the device in TFLOP/s (register-resident FFMA chains,
+ * `ms` milliseconds of work): the measured denominator of the voting roofline. */
+int visfd_cuda_fp32_peak(visfd_ctx *ctx, double ms, double *tflops);
+
+/* ---- threshold / mask maps -------------------------------------------------------- */
+#define VISFD_THRESH_SINGLE 1 /* in > a ? outB : outA           handlers.cpp:1049-1053 */
+#define VISFD_THRESH_2      2 /* Threshold2, lib/threshold/threshold.hpp:52-77         */
+#define VISFD_THRESH_4      4 /* Threshold4, lib/threshold/threshold.hpp:117-169       */
+#define VISFD_THRESH_GAUSS  5 /* SelectIntensityRangeGauss, threshold.hpp:248-258      */
+#define VISFD_RESCALE       6 /* out = out*t[0] + t[1],      handlers.cpp:1040-1043    */
+/* HandleThresholds inner loop (bin/filter_mrc/handlers.cpp:1037-1080) fused with the
+ * mask fill of bin/filter_mrc/filter_mrc.cpp:771-776 (applied when mask != NULL and
+ * use_masked_value != 0).  t[4]: thresholds (unused entries ignored). */
+int visfd_cuda_threshold(visfd_ctx *ctx, int64_t n_voxels, const float *in, float *out,
+                         int kind, const float t[4], float outA, float outB,
+                         const float *mask, int use_masked_value, float masked_value);
+/* AverageArr / StdDevArr (lib/visfd/visfd_utils.hpp:685-790), needed by -cl. */
+int visfd_cuda_mean_stddev(visfd_ctx *ctx, int64_t n_voxels, const float *in,
+                           const float *weights, float *mean_out, float *stddev_out);
+
+/* ---- scale-space blob detection ----------------------------------------------------- */
+/* BlobDog<float>: lib/visfd/feature.hpp:56-427.  Results are written to caller
+ * (HOST) buffers of `capacity` entries each: crds (capacity*3, voxel x,y,z),
+ * sigma, score; *n_minima / *n_maxima receive the full counts (which may exceed
+ * capacity).  Lists are ordered by (scale, z, y, x). */
+int visfd_cuda_blob_dog(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                        const float *src, const float *mask, const float *sigmas,
+                        int n_sigmas, float delta_sigma_over_sigma, float truncate_ratio,
+                        float minima_threshold, float maxima_threshold,
+                        int use_threshold_ratios, int64_t capacity, float *min_crds,
+                        float *min_sigma, float *min_score, int64_t *n_minima,
+                        float *max_crds, float *max_sigma, float *max_score,
+                        int64_t *n_maxima);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISFD_CUDA_H */

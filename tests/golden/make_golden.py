@@ -1,0 +1,179 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref).
+
+Run in the development container, where /root/reference exists:
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Every array written here is an output of the reference's own code (the header-only
+library instantiated by oracle/ref_shim.cpp, or the stock filter_mrc binary) on small
+seeded inputs.  The fixtures travel with the repo, so that on machines without
+/root/reference (the GPU box) the oracle port and the CUDA path are still pinned to
+the reference.  The inputs are stored too: nothing has to be regenerated to check.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle.pyoracle import Oracle, have  # noqa: E402
+from visfd_b200 import synth  # noqa: E402
+
+REFERENCE = os.environ.get("VISFD_REFERENCE", "/root/reference")
+
+
+def read_mrc(path):
+    """Minimal reader of the mrc_simple wire format."""
+    raw = open(path, "rb").read()
+    h = np.frombuffer(raw[:1024], np.int32)
+    nx, ny, nz, mode = int(h[0]), int(h[1]), int(h[2]), int(h[3])
+    dt = {0: np.uint8, 1: np.int16, 2: np.float32, 6: np.uint16}[mode]
+    a = np.frombuffer(raw[1024:1024 + nx * ny * nz * np.dtype(dt).itemsize], dt)
+    return a.reshape(nz, ny, nx).astype(np.float32)
+
+
+def main():
+    if not have("reference"):
+        raise SystemExit("oracle/_ref/libvisfd_ref.so missing: run `make -C oracle ref` first")
+    ref = Oracle("reference")
+    out = {}
+
+    # ---- Gaussian taps (GenFilterGauss1D) -------------------------------------------------
+    taps_cases = [(2.0, 5), (0.8269, 2), (3.0, 7), (8.0, 21), (9.5, 25), (12.8, 33), (1.0, 1), (0.0, 2)]
+    out["taps_cases"] = np.array(taps_cases, np.float64)
+    for k, (s, hw) in enumerate(taps_cases):
+        out[f"taps_{k}"] = ref.gen_gauss1d(s, hw)
+
+    # ---- separable filters on a ragged little volume --------------------------------------
+    shape = (11, 13, 17)
+    rng = np.random.default_rng(1)
+    vol = synth.tomogram(shape, seed=3) + rng.standard_normal(shape).astype(np.float32) * 0.1
+    mask = np.ones(shape, np.float32)
+    mask[:, :3, :] = 0.0
+    mask[4:7, 5:9, 6:12] = 0.0
+    mask[8:, 9:, 2:5] = 0.5          # weights, not just 0/1
+    out["vol"], out["mask"] = vol, mask
+    out["gauss_s1.3_hw3"], A = ref.apply_gauss(vol, 1.3, 3)
+    out["gauss_A"] = np.float32(A)
+    out["gauss_s1.3_hw3_nonorm"], _ = ref.apply_gauss(vol, 1.3, 3, normalize=False)
+    out["gauss_aniso"], _ = ref.apply_gauss(vol, (1.0, 2.0, 0.7), (2, 5, 1))
+    out["gauss_masked"], _ = ref.apply_gauss(vol, 1.3, 3, mask=mask)
+    out["gauss_masked_nonorm"], _ = ref.apply_gauss(vol, 1.3, 3, mask=mask, normalize=False)
+    out["gauss_wide"], _ = ref.apply_gauss(vol, 4.0, 10)   # half-width >= the image in z
+    out["dog"], a, b = ref.apply_dog(vol, 1.2, 1.92, 5)
+    out["dog_AB"] = np.array([a, b], np.float32)
+    out["log"], a, b = ref.apply_log(vol, 1.5, 0.02, 2.6482)
+    out["log_AB"] = np.array([a, b], np.float32)
+    out["log_masked"], _, _ = ref.apply_log(vol, 1.5, 0.02, 2.6482, mask=mask)
+
+    # ---- Hessian / eigen / cut -------------------------------------------------------------
+    g, h = ref.calc_hessian(vol, 1.1, 2.6482)
+    out["hess_grad"], out["hess_hess"] = g, h
+    gm, hm = ref.calc_hessian(vol, 1.1, 2.6482, mask=mask)
+    out["hess_grad_masked"], out["hess_hess_masked"] = gm, hm
+    for order in (0, 1):
+        sal, dire, ev = ref.hessian_eigen_score(h, order=order, score_kind=0)
+        out[f"ridge_sal_o{order}"], out[f"ridge_dir_o{order}"], out[f"ridge_ev_o{order}"] = sal, dire, ev
+    sal_lin, _, _ = ref.hessian_eigen_score(h, order=1, score_kind=1)
+    out["ridge_sal_linear"] = sal_lin
+    cut, thr = ref.saliency_cut(out["ridge_sal_o1"], 0.1, True)
+    out["cut_frac0.1"], out["cut_frac0.1_thr"] = cut, np.float32(thr)
+    cutm, thrm = ref.saliency_cut(out["ridge_sal_o1"], 0.25, True, mask=mask)
+    out["cut_frac0.25_masked"], out["cut_frac0.25_masked_thr"] = cutm, np.float32(thrm)
+
+    # ---- tensor voting -----------------------------------------------------------------------
+    hw, decay, disp = ref.tv_tables(2.4, np.sqrt(2.0))
+    out["tv_tables_hw"], out["tv_decay"], out["tv_disp"] = np.int32(hw), decay, disp
+    tshape = (14, 12, 16)
+    tvol = synth.tomogram(tshape, seed=5)
+    out["tv_vol"] = tvol
+    m = ref.membrane(tvol, 1.0, 2.6482, 1, 0.12, True, 2.4, 4, float(np.float32(np.sqrt(2.0))))
+    for k in ("hess_saliency", "direction", "tensor", "out"):
+        out["mem_" + k] = m[k]
+    out["mem_thr"] = np.float32(m["threshold"])
+    # explicit TVDenseStick with exponent 2 / generic exponent 3 / curves, and with masks
+    sal, dire = m["hess_saliency"], m["direction"]
+    out["tv_e2"] = ref.tv_dense_stick(sal, dire, 2.4, 2, float(np.float32(np.sqrt(2.0))))
+    out["tv_e3"] = ref.tv_dense_stick(sal, dire, 2.4, 3, float(np.float32(np.sqrt(2.0))))
+    out["tv_e4_curves"] = ref.tv_dense_stick(sal, dire, 2.4, 4, float(np.float32(np.sqrt(2.0))), curves=True)
+    tmask = np.ones(tshape, np.float32)
+    tmask[:, :, :3] = 0.0
+    tmask[5:9, 4:8, 8:12] = 0.0
+    out["tv_mask"] = tmask
+    out["tv_e4_masked"] = ref.tv_dense_stick(sal, dire, 2.4, 4, float(np.float32(np.sqrt(2.0))),
+                                             mask_src=tmask, mask_dst=tmask)
+    out["tv_score_planar"] = ref.tensor_score(m["tensor"], order=1, score_kind=0)
+    mm = ref.membrane(tvol, 1.0, 2.6482, 1, 0.12, True, 2.4, 4, float(np.float32(np.sqrt(2.0))), mask=tmask)
+    out["mem_masked_out"], out["mem_masked_thr"] = mm["out"], np.float32(mm["threshold"])
+    mx = ref.membrane(-tvol, 1.0, 2.6482, 0, 0.12, True, 2.4, 4, float(np.float32(np.sqrt(2.0))))
+    out["mem_maxima_out"] = mx["out"]
+
+    # ---- thresholds ------------------------------------------------------------------------------
+    x = np.linspace(-2, 3, 101).astype(np.float32)
+    out["thr_x"] = x
+    out["thr1"] = ref.threshold1(x, 0.5, 0.0, 1.0)
+    out["thr2_up"] = ref.threshold2(x, 0.2, 1.4, 0.0, 1.0)
+    out["thr2_down"] = ref.threshold2(x, 1.4, 0.2, -1.0, 2.0)
+    out["thr4"] = ref.threshold4(x, -1.0, -0.5, 1.5, 2.0, 0.0, 1.0)
+    out["thr4_rev"] = ref.threshold4(x, 2.0, 1.5, -0.5, -1.0, 0.0, 1.0)
+    out["mean_std"] = np.array([ref.average(vol), ref.stddev(vol), ref.average(vol, mask), ref.stddev(vol, mask)],
+                               np.float32)
+
+    # ---- blobs --------------------------------------------------------------------------------------
+    bshape = (28, 30, 32)
+    bvol = synth.tomogram(bshape, seed=9, blobs=10, noise=0.1, n_shells=0, blob_sigma=(1.5, 2.5))
+    out["blob_vol"] = bvol
+    sig = 1.0 * (1.25 ** np.arange(6))
+    out["blob_sigmas"] = sig.astype(np.float32)
+    mn, mx_ = ref.blob_dog(bvol, sig, 0.02, 2.6482, minima_threshold=0.0, maxima_threshold=-np.inf,
+                           use_threshold_ratios=False)
+    out["blob_minima"], out["blob_maxima"] = mn, mx_
+    mn2, mx2 = ref.blob_dog(bvol, sig, 0.02, 2.6482, minima_threshold=0.5, maxima_threshold=0.5,
+                            use_threshold_ratios=True)
+    out["blob_minima_ratio"], out["blob_maxima_ratio"] = mn2, mx2
+
+    # ---- C1: the reference's own membrane test, run by the stock filter_mrc binary -----------------
+    fm = os.path.join(ROOT, "oracle", "_ref", "filter_mrc")
+    fixture = os.path.join(REFERENCE, "tests", "test_image_membrane.rec")
+    if os.path.exists(fm) and os.path.exists(fixture):
+        raw = read_mrc(fixture)
+        binned = raw.reshape(8, 2, 8, 2, 8, 2).sum(axis=(1, 3, 5), dtype=np.float32) / np.float32(8)
+        with tempfile.TemporaryDirectory() as td:
+            o = os.path.join(td, "out.rec")
+            # tests/test_membrane_detection.sh:8 without -save-progress
+            subprocess.run([fm, "-w", "19.2", "-in", fixture, "-out", o, "-membrane", "minima", "55", "-tv", "4",
+                            "-tv-angle-exponent", "4", "-bin", "2"], check=True, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL)
+            c1 = read_mrc(o)
+            o2 = os.path.join(td, "out_notv.rec")
+            subprocess.run([fm, "-w", "19.2", "-in", fixture, "-out", o2, "-membrane", "minima", "55", "-bin", "2"],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            c1n = read_mrc(o2)
+        # parameters exactly as settings.cpp / filter_mrc.cpp derive them (float arithmetic)
+        vw = np.float32(19.2) * np.float32(2)
+        sigma = np.float32(np.float32(55.0) / np.sqrt(3.0))
+        tv_sigma = np.float32(np.float32(4.0) * sigma)
+        sigma = np.float32(sigma / vw)
+        tv_sigma = np.float32(tv_sigma / vw)
+        ratio = np.float32(np.sqrt(np.float32(-2) * np.log(np.float32(0.03))))
+        out["c1_in_binned"] = binned
+        out["c1_params"] = np.array([sigma, ratio, tv_sigma, 4, np.float32(np.sqrt(2.0)), 0.05], np.float32)
+        out["c1_out"] = c1
+        out["c1_out_notv"] = c1n
+        # cross-check: the library path with these parameters reproduces the CLI bit for bit
+        chk = ref.membrane(binned, float(sigma), float(ratio), 1, 0.05, True, float(tv_sigma), 4,
+                           float(np.float32(np.sqrt(2.0))))
+        assert np.array_equal(chk["out"], c1), "C1: library replay differs from filter_mrc output"
+        print("C1: sum=%.6e max=%.6e nonzero=%d" % (c1.sum(dtype=np.float64), c1.max(), (c1 != 0).sum()))
+
+    path = os.path.join(HERE, "reference_vectors.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KiB" % (os.path.getsize(path) / 1024), len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,387 @@
+"""GPU parity: every C-ABI entry point of libvisfd_cuda.so against the CPU oracle on the
+same seeded inputs, and against the committed reference vectors.
+
+Tolerances (BASELINE.json:north_star): 1e-5 relative for Gaussian/DoG/LoG outputs,
+1e-4 for saliency and vote outputs, normals up to sign, masks / blob lists / index work
+bit-exact.  "Relative" is util.rel_err: per-voxel |a-b| / max(|b|, 1e-3 * max|b|).
+"""
+import numpy as np
+import pytest
+
+from util import TOL_GAUSS, TOL_SALIENCY, rel_err, tensor_rel_err, direction_err, sort_blobs
+from visfd_b200 import synth
+import visfd_b200 as vb
+
+pytestmark = pytest.mark.gpu
+SQ2 = float(np.float32(np.sqrt(2.0)))
+
+
+def test_library_is_the_cuda_one(ctx):
+    import ctypes
+    assert ctx.lib.visfd_cuda_version() >= 1
+    n0 = ctx.launch_count()
+    ctx.apply_gauss(np.ones((4, 4, 4), np.float32), 1.0, 1)
+    assert ctx.launch_count() - n0 == 3  # Z, Y, X sweeps
+
+
+def test_no_fallback_error_paths(ctx):
+    with pytest.raises(vb.VisfdCudaError):
+        ctx.calc_hessian(np.zeros((2, 5, 5), np.float32), 1.0, 2.5)   # feature.hpp:1260-1264
+    with pytest.raises(vb.VisfdCudaError):
+        ctx.tv_dense_stick(np.zeros((4, 4, 4), np.float32), np.zeros((4, 4, 4, 3), np.float32), -1.0, 4, SQ2)
+
+
+# ---- taps (host code of the library) -------------------------------------------------------
+def test_taps_bit_exact(golden, oracle):
+    for k, (s, hw) in enumerate(golden["taps_cases"]):
+        assert np.array_equal(vb.gen_gauss1d(float(s), int(hw)), golden[f"taps_{k}"])
+    for s in (0.5, 1.7, 3.0, 7.13, 10.0, 10.5):
+        hw = vb.gauss_halfwidth(s, -1.0, 0.03)
+        assert np.array_equal(vb.gen_gauss1d(s, hw), oracle.gen_gauss1d(s, hw))
+
+
+# ---- separable filters -----------------------------------------------------------------------
+def test_gauss_golden(ctx, golden):
+    vol, mask = golden["vol"], golden["mask"]
+    d, A = ctx.apply_gauss(vol, 1.3, 3)
+    assert rel_err(d, golden["gauss_s1.3_hw3"]) <= TOL_GAUSS
+    assert np.float32(A) == golden["gauss_A"]
+    assert rel_err(ctx.apply_gauss(vol, 1.3, 3, normalize=False)[0], golden["gauss_s1.3_hw3_nonorm"]) <= TOL_GAUSS
+    assert rel_err(ctx.apply_gauss(vol, (1.0, 2.0, 0.7), (2, 5, 1))[0], golden["gauss_aniso"]) <= TOL_GAUSS
+    assert rel_err(ctx.apply_gauss(vol, 1.3, 3, mask=mask)[0], golden["gauss_masked"]) <= TOL_GAUSS
+    assert rel_err(ctx.apply_gauss(vol, 1.3, 3, mask=mask, normalize=False)[0],
+                   golden["gauss_masked_nonorm"]) <= TOL_GAUSS
+    assert rel_err(ctx.apply_gauss(vol, 4.0, 10)[0], golden["gauss_wide"]) <= TOL_GAUSS
+    d, a, b = ctx.apply_dog(vol, 1.2, 1.92, 5)
+    assert rel_err(d, golden["dog"]) <= TOL_GAUSS
+    assert np.array_equal(np.array([a, b], np.float32), golden["dog_AB"])
+    d, a, b = ctx.apply_log(vol, 1.5, 0.02, 2.6482)
+    assert rel_err(d, golden["log"]) <= 20 * TOL_GAUSS  # see test_log_cancellation
+    np.testing.assert_allclose(np.array([a, b], np.float32), golden["log_AB"], rtol=1e-6)
+    assert rel_err(ctx.apply_log(vol, 1.5, 0.02, 2.6482, mask=mask)[0], golden["log_masked"]) <= 20 * TOL_GAUSS
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 1, 2), (5, 7, 130), (70, 9, 33), (9, 140, 7), (64, 64, 128),
+                                   (67, 65, 131)])
+@pytest.mark.parametrize("sigma,hw", [(1.0, 2), (3.0, 7), (8.0, 21)])
+def test_gauss_shapes(ctx, oracle, shape, sigma, hw):
+    """ragged / degenerate shapes, half-widths beyond the image, unaligned x (scalar tail path)"""
+    vol = synth.tomogram(shape, seed=1) if min(shape) > 1 else np.random.default_rng(0).standard_normal(
+        shape).astype(np.float32)
+    want, A0 = oracle.apply_gauss(vol, sigma, hw)
+    got, A1 = ctx.apply_gauss(vol, sigma, hw)
+    assert rel_err(got, want) <= TOL_GAUSS
+    assert np.float32(A0) == np.float32(A1)
+
+
+def test_gauss_masked_and_device_path(ctx, oracle):
+    import torch
+    vol = synth.tomogram((40, 50, 72), seed=2)
+    rng = np.random.default_rng(3)
+    mask = (rng.random(vol.shape) > 0.3).astype(np.float32)
+    mask[rng.random(vol.shape) > 0.9] = 0.5
+    for normalize in (True, False):
+        want, _ = oracle.apply_gauss(vol, 2.0, 5, mask=mask, normalize=normalize)
+        got, _ = ctx.apply_gauss(vol, 2.0, 5, mask=mask, normalize=normalize)
+        assert rel_err(got, want) <= TOL_GAUSS
+        # device-resident path: same kernels, no staging
+        got_d, _ = ctx.apply_gauss(torch.from_numpy(vol).cuda(), 2.0, 5, mask=torch.from_numpy(mask).cuda(),
+                                   normalize=normalize)
+        assert np.array_equal(got_d.cpu().numpy(), got)
+    # explicit taps (ApplySeparable)
+    tx, ty, tz = (vb.gen_gauss1d(s, h) for s, h in ((1.0, 3), (2.5, 6), (0.7, 2)))
+    want, _ = oracle.apply_gauss(vol, (1.0, 2.5, 0.7), (3, 6, 2))
+    got, _ = ctx.apply_separable(vol, (tx, ty, tz))
+    assert rel_err(got, want) <= TOL_GAUSS
+
+
+def test_dog_log(ctx, oracle):
+    vol = synth.tomogram((48, 40, 56), seed=4)
+    want, a0, b0 = oracle.apply_dog(vol, 2.0, 3.2, 8)
+    got, a1, b1 = ctx.apply_dog(vol, 2.0, 3.2, 8)
+    assert rel_err(got, want) <= TOL_GAUSS
+    assert (np.float32(a0), np.float32(b0)) == (np.float32(a1), np.float32(b1))
+
+
+def test_log_cancellation(ctx, oracle):
+    """ApplyLog subtracts two Gaussians that differ by 2 % in sigma and multiplies by
+    1/delta^2 = 2500: a 1e-7 rounding difference in either Gaussian is a ~1e-4 relative
+    difference of the result.  The Gaussians themselves meet 1e-5; the LoG is judged at
+    the tolerance that follows from it and against the reference's own sensitivity."""
+    vol = synth.tomogram((40, 44, 48), seed=6, blobs=4)
+    want, _, _ = oracle.apply_log(vol, 2.0, 0.02, 2.6482)
+    got, _, _ = ctx.apply_log(vol, 2.0, 0.02, 2.6482)
+    assert rel_err(got, want) <= 2e-4
+    # scale check: the reference's own response to a 1-ulp perturbation of its input
+    pert = np.nextafter(vol, np.float32(np.inf))
+    want_p, _, _ = oracle.apply_log(pert, 2.0, 0.02, 2.6482)
+    assert rel_err(got, want) <= 50 * max(rel_err(want_p, want), 1e-6)
+
+
+def test_gauss_linearity_and_constant(ctx):
+    """size-independent properties at a larger size: linearity; a constant image stays
+    constant under the normalised filter (borders included)."""
+    shape = (96, 160, 256)
+    a = synth.tomogram(shape, seed=7)
+    b = synth.tomogram(shape, seed=8)
+    ga, _ = ctx.apply_gauss(a, 3.0, 7)
+    gb, _ = ctx.apply_gauss(b, 3.0, 7)
+    gab, _ = ctx.apply_gauss(a + 2 * b, 3.0, 7)
+    assert rel_err(gab, ga + 2 * gb) <= 2e-5
+    gc, _ = ctx.apply_gauss(np.full(shape, 3.25, np.float32), 3.0, 7)
+    assert np.abs(gc - 3.25).max() <= 3.25 * 1e-6
+
+
+def test_gauss_slab_equals_whole(ctx):
+    import torch
+    shape = (60, 40, 72)
+    vol = synth.tomogram(shape, seed=9)
+    whole, _ = ctx.apply_gauss(vol, 2.0, 5)
+    z0, z1, halo = 20, 41, 5
+    lo, hi = z0 - halo, z1 + halo
+    slab, _ = ctx.apply_gauss(vol[lo:hi].copy(), 2.0, 5, z_offset=lo, nz_global=shape[0])
+    assert np.array_equal(slab[halo:halo + (z1 - z0)], whole[z0:z1])
+    # a slab touching the global border reproduces the border normalisation
+    slab0, _ = ctx.apply_gauss(vol[:30].copy(), 2.0, 5, z_offset=0, nz_global=shape[0])
+    assert np.array_equal(slab0[:25], whole[:25])
+
+
+# ---- Hessian / eigen / saliency ------------------------------------------------------------------
+def test_calc_hessian(ctx, oracle, golden):
+    vol, mask = golden["vol"], golden["mask"]
+    g, h = ctx.calc_hessian(vol, 1.1, 2.6482)
+    assert rel_err(g, golden["hess_grad"]) <= 1e-4
+    assert rel_err(h, golden["hess_hess"]) <= 1e-4
+    g, h = ctx.calc_hessian(vol, 1.1, 2.6482, mask=mask)
+    assert rel_err(g, golden["hess_grad_masked"]) <= 1e-4
+    assert rel_err(h, golden["hess_hess_masked"]) <= 1e-4
+    assert np.all(h[mask == 0] == 0)
+
+
+def test_tensor_score_matches_reference_eigen(ctx, oracle, golden):
+    """the eigensolver alone, on the reference's own Hessians: float eigenvalues and scores"""
+    h = golden["hess_hess"]
+    for order in (0, 1):
+        sal, ev, dire = ctx.tensor_score(h, order=order, score_kind=vb.SCORE_PLANAR, is_vote_tensor=False,
+                                         want_eivals=True, want_direction=True)
+        assert rel_err(ev, golden[f"ridge_ev_o{order}"]) <= 1e-6
+        assert rel_err(sal, golden[f"ridge_sal_o{order}"]) <= 1e-5
+        # normals only where the top eigenvalue is separated (degenerate voxels have none)
+        evr = golden[f"ridge_ev_o{order}"].astype(np.float64)
+        gap = np.abs(evr[..., 0] - evr[..., 1]) / np.abs(evr).max()
+        assert direction_err(dire, golden[f"ridge_dir_o{order}"], weight=gap > 1e-3) <= 1e-5
+    sal, _, _ = ctx.tensor_score(h, order=1, score_kind=vb.SCORE_LINEAR, is_vote_tensor=False)
+    assert rel_err(sal, golden["ridge_sal_linear"]) <= 1e-5
+    sc, _, _ = ctx.tensor_score(golden["mem_tensor"], order=1, score_kind=vb.SCORE_PLANAR, is_vote_tensor=True)
+    assert rel_err(sc, golden["tv_score_planar"]) <= 1e-5
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_hessian_ridge(ctx, oracle, order):
+    vol = synth.tomogram((36, 44, 52), seed=10)
+    if order == 0:
+        vol = -vol
+    g, h = oracle.calc_hessian(vol, 2.0, 2.6482)
+    want_sal, want_dir, want_ev = oracle.hessian_eigen_score(h, order=order)
+    sal, dire = ctx.hessian_ridge(vol, 2.0, 2.6482, order=order)
+    assert rel_err(sal, want_sal) <= TOL_SALIENCY
+    strong = want_sal > 1e-3 * want_sal.max()
+    assert direction_err(dire, want_dir, weight=strong) <= 1e-4
+
+
+def test_hessian_ridge_masked(ctx, oracle):
+    vol = synth.tomogram((30, 34, 40), seed=12)
+    mask = np.ones(vol.shape, np.float32)
+    mask[:, :, :9] = 0
+    mask[10:20, 10:20, 20:30] = 0
+    g, h = oracle.calc_hessian(vol, 1.5, 2.6482, mask=mask)
+    want_sal, want_dir, _ = oracle.hessian_eigen_score(h, order=1, mask=mask)
+    sal, dire = ctx.hessian_ridge(vol, 1.5, 2.6482, order=1, mask=mask)
+    assert rel_err(sal, want_sal) <= TOL_SALIENCY
+    assert np.all(sal[mask == 0] == 0)
+
+
+# ---- saliency cut ----------------------------------------------------------------------------------
+def test_saliency_cut_bit_exact(ctx, oracle, golden):
+    sal = golden["ridge_sal_o1"]
+    out, thr = ctx.saliency_cut(sal, 0.1, True)
+    assert np.float32(thr) == golden["cut_frac0.1_thr"] and np.array_equal(out, golden["cut_frac0.1"])
+    out, thr = ctx.saliency_cut(sal, 0.25, True, mask=golden["mask"])
+    assert np.float32(thr) == golden["cut_frac0.25_masked_thr"]
+    assert np.array_equal(out, golden["cut_frac0.25_masked"])
+    out, thr = ctx.saliency_cut(sal, float(golden["cut_frac0.1_thr"]), False)
+    assert np.array_equal(out, golden["cut_frac0.1"])
+
+
+@pytest.mark.parametrize("n,frac", [(1, 0.05), (37, 0.5), (100003, 0.05), (1 << 20, 0.013), (300007, 0.999)])
+def test_radix_select_matches_sort(ctx, oracle, n, frac):
+    rng = np.random.default_rng(n)
+    v = (rng.standard_normal(n) ** 2 * 1e9).astype(np.float32)
+    v[rng.random(n) < 0.1] = 0.0                         # ties
+    v[rng.random(n) < 0.05] = v[0]
+    if n > 100:
+        v[:50] = -v[:50]                                 # negative keys too
+    want, thr0 = oracle.saliency_cut(v, frac, True)
+    got, thr1 = ctx.saliency_cut(v, frac, True)
+    assert np.float32(thr0) == np.float32(thr1)
+    assert np.array_equal(got, want)
+    again, _ = ctx.saliency_cut(got, thr1, False)        # idempotent
+    assert np.array_equal(again, got)
+
+
+# ---- tensor voting -------------------------------------------------------------------------------------
+def test_tv_golden(ctx, golden):
+    sal, dire = golden["mem_hess_saliency"], golden["mem_direction"]
+    assert tensor_rel_err(ctx.tv_dense_stick(sal, dire, 2.4, 4, SQ2), golden["mem_tensor"]) <= TOL_SALIENCY
+    assert tensor_rel_err(ctx.tv_dense_stick(sal, dire, 2.4, 2, SQ2), golden["tv_e2"]) <= TOL_SALIENCY
+    assert tensor_rel_err(ctx.tv_dense_stick(sal, dire, 2.4, 3, SQ2), golden["tv_e3"]) <= TOL_SALIENCY
+    assert tensor_rel_err(ctx.tv_dense_stick(sal, dire, 2.4, 4, SQ2, curves=True),
+                          golden["tv_e4_curves"]) <= TOL_SALIENCY
+    tm = golden["tv_mask"]
+    got = ctx.tv_dense_stick(sal, dire, 2.4, 4, SQ2, mask_src=tm, mask_dst=tm)
+    assert tensor_rel_err(got, golden["tv_e4_masked"]) <= TOL_SALIENCY
+    assert np.all(got[tm == 0] == 0)
+
+
+@pytest.mark.parametrize("sigma_tv,shape", [(2.9, (20, 24, 28)), (7.08, (30, 33, 41)), (14.2, (44, 48, 50))])
+def test_tv_radii(ctx, oracle, sigma_tv, shape):
+    """vote radii 4, 10 and 20 (hw = floor(sigma*sqrt2)); includes the lattice points that
+    sit exactly on the support shell r^2 == hw^2"""
+    vol = synth.tomogram(shape, seed=13)
+    m = oracle.membrane(vol, 1.5, 2.6482, 1, 0.05, True, 0.0, 4, SQ2)
+    sal, dire = m["hess_saliency"], m["direction"]
+    want = oracle.tv_dense_stick(sal, dire, sigma_tv, 4, SQ2)
+    got = ctx.tv_dense_stick(sal, dire, sigma_tv, 4, SQ2)
+    assert tensor_rel_err(got, want) <= TOL_SALIENCY
+    hw = vb.tv_halfwidth(sigma_tv, SQ2)
+    pairs = ctx.tv_count_pairs(sal, -np.inf, hw)
+    assert pairs > 0
+
+
+def test_tv_single_voter_support(ctx, oracle):
+    """one voter: the support is exactly the reference's truncated table (shell included)"""
+    for sigma_tv in (2.9, 3.6, 5.0, 7.08):
+        hw = vb.tv_halfwidth(sigma_tv, SQ2)
+        n = 2 * hw + 5
+        sal = np.zeros((n, n, n), np.float32)
+        dire = np.zeros((n, n, n, 3), np.float32)
+        c = n // 2
+        sal[c, c, c] = 2.0
+        dire[c, c, c] = (0.6, 0.0, 0.8)
+        want = oracle.tv_dense_stick(sal, dire, sigma_tv, 4, SQ2)
+        got = ctx.tv_dense_stick(sal, dire, sigma_tv, 4, SQ2)
+        tw, tg = np.abs(want).sum(-1), np.abs(got).sum(-1)
+        assert np.array_equal(tw != 0, tg != 0)
+        assert tensor_rel_err(got, want) <= TOL_SALIENCY
+
+
+def test_membrane_golden_and_c1(ctx, golden):
+    tvol = golden["tv_vol"]
+    m = ctx.membrane(tvol, 1.0, 2.6482, 1, 0.12, True, 2.4, 4, SQ2, want_saliency=True, want_direction=True,
+                     want_tensor=True)
+    assert np.float32(m["threshold"]) == golden["mem_thr"] or rel_err(m["threshold"], golden["mem_thr"]) <= 1e-5
+    kept_ref = golden["mem_hess_saliency"] != 0
+    assert np.array_equal(m["hess_saliency"] != 0, kept_ref)       # same survivors
+    assert rel_err(m["hess_saliency"], golden["mem_hess_saliency"]) <= TOL_SALIENCY
+    assert direction_err(m["direction"], golden["mem_direction"], weight=kept_ref) <= 1e-4
+    assert tensor_rel_err(m["tensor"], golden["mem_tensor"]) <= TOL_SALIENCY
+    assert rel_err(m["out"], golden["mem_out"]) <= TOL_SALIENCY
+    # same call without the optional outputs takes the recompute-directions path
+    m2 = ctx.membrane(tvol, 1.0, 2.6482, 1, 0.12, True, 2.4, 4, SQ2)
+    assert rel_err(m2["out"], golden["mem_out"]) <= TOL_SALIENCY
+    mm = ctx.membrane(tvol, 1.0, 2.6482, 1, 0.12, True, 2.4, 4, SQ2, mask=golden["tv_mask"])
+    assert rel_err(mm["out"], golden["mem_masked_out"]) <= TOL_SALIENCY
+    mx = ctx.membrane(-tvol, 1.0, 2.6482, 0, 0.12, True, 2.4, 4, SQ2)
+    assert rel_err(mx["out"], golden["mem_maxima_out"]) <= TOL_SALIENCY
+    # BASELINE config 1 (the reference's own test, output of the stock filter_mrc binary)
+    sigma, ratio, tv_sigma, expo, tv_ratio, frac = [float(v) for v in golden["c1_params"]]
+    c1 = ctx.membrane(golden["c1_in_binned"], sigma, ratio, 1, frac, True, tv_sigma, int(expo), tv_ratio)
+    assert rel_err(c1["out"], golden["c1_out"]) <= TOL_SALIENCY
+    assert (c1["out"] != 0).sum() == 419
+    assert abs(c1["out"].sum(dtype=np.float64) / 4.141152e11 - 1) < 1e-5
+    c1n = ctx.membrane(golden["c1_in_binned"], sigma, ratio, 1, frac, True, 0.0, int(expo), tv_ratio)
+    assert rel_err(c1n["out"], golden["c1_out_notv"]) <= TOL_SALIENCY
+    assert (c1n["out"] != 0).sum() == 27
+
+
+def test_membrane_pipeline_vs_oracle(ctx, oracle):
+    """the C4 parameter set (sigma 3, hw_gauss 7, sigma_tv 14.2, hw_tv 20, exponent 4,
+    -tv-best 0.05) on a volume the oracle finishes in seconds"""
+    vol = synth.tomogram((56, 60, 64), seed=14, n_shells=2)
+    sigma, ratio, tv_sigma = 2.99991, 2.6482, 14.1986
+    want = oracle.membrane(vol, sigma, ratio, 1, 0.05, True, tv_sigma, 4, SQ2, want_tensor=False)
+    got = ctx.membrane(vol, sigma, ratio, 1, 0.05, True, tv_sigma, 4, SQ2, want_saliency=True)
+    assert rel_err(got["threshold"], want["threshold"]) <= TOL_SALIENCY
+    # survivors of the cut: identical except voxels within tolerance of the threshold
+    thr = want["threshold"]
+    differ = (got["hess_saliency"] != 0) != (want["hess_saliency"] != 0)
+    pre = oracle.membrane(vol, sigma, ratio, 1, 0.0, False, 0.0, 4, SQ2)["out"]
+    assert np.all(np.abs(pre[differ] - thr) <= TOL_SALIENCY * thr)
+    if not differ.any():
+        assert rel_err(got["out"], want["out"]) <= TOL_SALIENCY
+
+
+def test_membrane_device_path_identical(ctx):
+    import torch
+    vol = synth.tomogram((40, 40, 48), seed=15)
+    a = ctx.membrane(vol, 2.0, 2.6482, 1, 0.05, True, 5.0, 4, SQ2)
+    b = ctx.membrane(torch.from_numpy(vol).cuda(), 2.0, 2.6482, 1, 0.05, True, 5.0, 4, SQ2)
+    assert np.array_equal(a["out"], b["out"].cpu().numpy())
+    assert ctx.last_voter_count() > 0
+
+
+# ---- thresholds -----------------------------------------------------------------------------------------
+def test_thresholds_bit_exact(ctx, oracle, golden):
+    x = golden["thr_x"]
+    assert np.array_equal(ctx.threshold(x, vb.THRESH_SINGLE, [0.5]), golden["thr1"])
+    assert np.array_equal(ctx.threshold(x, vb.THRESH_2, [0.2, 1.4]), golden["thr2_up"])
+    assert np.array_equal(ctx.threshold(x, vb.THRESH_2, [1.4, 0.2], -1.0, 2.0), golden["thr2_down"])
+    assert np.array_equal(ctx.threshold(x, vb.THRESH_4, [-1.0, -0.5, 1.5, 2.0]), golden["thr4"])
+    assert np.array_equal(ctx.threshold(x, vb.THRESH_4, [2.0, 1.5, -0.5, -1.0]), golden["thr4_rev"])
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(100001).astype(np.float32)
+    mask = (rng.random(v.size) > 0.5).astype(np.float32)
+    want = oracle.threshold2(v, -0.3, 0.8, 0.0, 1.0)
+    got = ctx.threshold(v, vb.THRESH_2, [-0.3, 0.8], mask=mask, masked_value=-7.0)
+    assert np.array_equal(got[mask != 0], want[mask != 0]) and np.all(got[mask == 0] == -7.0)
+    r = ctx.threshold(None, vb.RESCALE, [2.0, 1.0], out=v.copy())
+    assert np.array_equal(r, v * np.float32(2.0) + np.float32(1.0))
+    empty = ctx.threshold(np.zeros(0, np.float32), vb.THRESH_SINGLE, [0.0])
+    assert empty.size == 0
+
+
+def test_mean_stddev(ctx, golden):
+    vol, mask = golden["vol"], golden["mask"]
+    m, s = ctx.mean_stddev(vol)
+    mw, sw = ctx.mean_stddev(vol, mask)
+    np.testing.assert_allclose([m, s, mw, sw], golden["mean_std"], rtol=2e-6)
+
+
+# ---- blobs ---------------------------------------------------------------------------------------------------
+def test_blob_dog_lists_exact(ctx, oracle, golden):
+    bvol, sig = golden["blob_vol"], golden["blob_sigmas"]
+    for kw, names in ((dict(minima_threshold=0.0, maxima_threshold=-np.inf, use_threshold_ratios=False),
+                       ("blob_minima", "blob_maxima")),
+                      (dict(minima_threshold=0.5, maxima_threshold=0.5, use_threshold_ratios=True),
+                       ("blob_minima_ratio", "blob_maxima_ratio"))):
+        mn, mx = ctx.blob_dog(bvol, sig, 0.02, 2.6482, **kw)
+        for got, name in ((mn, names[0]), (mx, names[1])):
+            want = sort_blobs(golden[name])
+            got = sort_blobs(got)
+            assert got.shape == want.shape
+            assert np.array_equal(got[:, :4], want[:, :4])              # positions and scales: exact
+            np.testing.assert_allclose(got[:, 4], want[:, 4], rtol=2e-4)  # LoG scores (see test_log_cancellation)
+
+
+def test_blob_dog_masked_vs_oracle(ctx, oracle):
+    vol = synth.tomogram((30, 34, 38), seed=16, blobs=12, noise=0.1, n_shells=0, blob_sigma=(1.5, 2.5))
+    mask = np.ones(vol.shape, np.float32)
+    mask[:, :8, :] = 0
+    sig = 1.0 * 1.25 ** np.arange(6)
+    want = oracle.blob_dog(vol, sig, 0.02, 2.6482, mask=mask, minima_threshold=0.0, maxima_threshold=-np.inf,
+                           use_threshold_ratios=False)
+    got = ctx.blob_dog(vol, sig, 0.02, 2.6482, mask=mask, minima_threshold=0.0, maxima_threshold=-np.inf,
+                       use_threshold_ratios=False)
+    for g, w in zip(got, want):
+        g, w = sort_blobs(g), sort_blobs(w)
+        assert g.shape == w.shape and np.array_equal(g[:, :4], w[:, :4])

@@ -1,0 +1,151 @@
+"""Pins the CPU oracle (oracle/visfd_oracle.cpp, our restatement) to the reference:
+against tests/golden/reference_vectors.npz (outputs of the unmodified reference, see
+tests/golden/make_golden.py) everywhere, and against oracle/_ref itself where it has
+been built.  Same compiler + libm => the restatement is expected to be BIT-identical.
+"""
+import numpy as np
+import pytest
+
+from util import sort_blobs
+
+SQ2 = float(np.float32(np.sqrt(2.0)))
+
+
+def eq(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    assert np.array_equal(a, b), f"max |diff| = {np.abs(a.astype(np.float64) - b).max()}"
+
+
+def test_taps(oracle, golden):
+    for k, (s, hw) in enumerate(golden["taps_cases"]):
+        eq(oracle.gen_gauss1d(float(s), int(hw)), golden[f"taps_{k}"])
+    # SURVEY.md 8c bootstrap value: GenFilterGauss1D(2.0, 5)
+    t = oracle.gen_gauss1d(2.0, 5)
+    np.testing.assert_allclose(t[:6], [0.00931539, 0.0261393, 0.0615941, 0.11853, 0.180124, 0.208593], rtol=1e-5)
+    assert abs(t.sum() - 1.0) < 1e-6 and np.array_equal(t, t[::-1])
+
+
+def test_separable(oracle, golden):
+    vol, mask = golden["vol"], golden["mask"]
+    d, A = oracle.apply_gauss(vol, 1.3, 3)
+    eq(d, golden["gauss_s1.3_hw3"])
+    assert np.float32(A) == golden["gauss_A"]
+    eq(oracle.apply_gauss(vol, 1.3, 3, normalize=False)[0], golden["gauss_s1.3_hw3_nonorm"])
+    eq(oracle.apply_gauss(vol, (1.0, 2.0, 0.7), (2, 5, 1))[0], golden["gauss_aniso"])
+    eq(oracle.apply_gauss(vol, 1.3, 3, mask=mask)[0], golden["gauss_masked"])
+    eq(oracle.apply_gauss(vol, 1.3, 3, mask=mask, normalize=False)[0], golden["gauss_masked_nonorm"])
+    eq(oracle.apply_gauss(vol, 4.0, 10)[0], golden["gauss_wide"])
+    d, a, b = oracle.apply_dog(vol, 1.2, 1.92, 5)
+    eq(d, golden["dog"])
+    eq(np.array([a, b], np.float32), golden["dog_AB"])
+    d, a, b = oracle.apply_log(vol, 1.5, 0.02, 2.6482)
+    eq(d, golden["log"])
+    eq(np.array([a, b], np.float32), golden["log_AB"])
+    eq(oracle.apply_log(vol, 1.5, 0.02, 2.6482, mask=mask)[0], golden["log_masked"])
+
+
+def test_hessian_eigen_cut(oracle, golden):
+    vol, mask = golden["vol"], golden["mask"]
+    g, h = oracle.calc_hessian(vol, 1.1, 2.6482)
+    eq(g, golden["hess_grad"])
+    eq(h, golden["hess_hess"])
+    g, h2 = oracle.calc_hessian(vol, 1.1, 2.6482, mask=mask)
+    eq(g, golden["hess_grad_masked"])
+    eq(h2, golden["hess_hess_masked"])
+    for order in (0, 1):
+        sal, dire, ev = oracle.hessian_eigen_score(h, order=order, score_kind=0)
+        eq(sal, golden[f"ridge_sal_o{order}"])
+        eq(dire, golden[f"ridge_dir_o{order}"])
+        eq(ev, golden[f"ridge_ev_o{order}"])
+    eq(oracle.hessian_eigen_score(h, order=1, score_kind=1)[0], golden["ridge_sal_linear"])
+    cut, thr = oracle.saliency_cut(golden["ridge_sal_o1"], 0.1, True)
+    eq(cut, golden["cut_frac0.1"])
+    assert np.float32(thr) == golden["cut_frac0.1_thr"]
+    cut, thr = oracle.saliency_cut(golden["ridge_sal_o1"], 0.25, True, mask=mask)
+    eq(cut, golden["cut_frac0.25_masked"])
+    assert np.float32(thr) == golden["cut_frac0.25_masked_thr"]
+    with pytest.raises(ValueError):
+        oracle.calc_hessian(np.zeros((2, 5, 5), np.float32), 1.0, 2.5)
+
+
+def test_tensor_voting(oracle, golden):
+    hw, decay, disp = oracle.tv_tables(2.4, np.sqrt(2.0))
+    assert hw == int(golden["tv_tables_hw"])
+    eq(decay, golden["tv_decay"])
+    eq(disp, golden["tv_disp"])
+    tvol = golden["tv_vol"]
+    m = oracle.membrane(tvol, 1.0, 2.6482, 1, 0.12, True, 2.4, 4, SQ2)
+    for k in ("hess_saliency", "direction", "tensor", "out"):
+        eq(m[k], golden["mem_" + k])
+    assert np.float32(m["threshold"]) == golden["mem_thr"]
+    sal, dire = golden["mem_hess_saliency"], golden["mem_direction"]
+    eq(oracle.tv_dense_stick(sal, dire, 2.4, 2, SQ2), golden["tv_e2"])
+    eq(oracle.tv_dense_stick(sal, dire, 2.4, 3, SQ2), golden["tv_e3"])
+    eq(oracle.tv_dense_stick(sal, dire, 2.4, 4, SQ2, curves=True), golden["tv_e4_curves"])
+    tm = golden["tv_mask"]
+    eq(oracle.tv_dense_stick(sal, dire, 2.4, 4, SQ2, mask_src=tm, mask_dst=tm), golden["tv_e4_masked"])
+    eq(oracle.tensor_score(golden["mem_tensor"], order=1, score_kind=0), golden["tv_score_planar"])
+    mm = oracle.membrane(tvol, 1.0, 2.6482, 1, 0.12, True, 2.4, 4, SQ2, mask=tm)
+    eq(mm["out"], golden["mem_masked_out"])
+    mx = oracle.membrane(-tvol, 1.0, 2.6482, 0, 0.12, True, 2.4, 4, SQ2)
+    eq(mx["out"], golden["mem_maxima_out"])
+
+
+def test_thresholds(oracle, golden):
+    x = golden["thr_x"]
+    eq(oracle.threshold1(x, 0.5, 0.0, 1.0), golden["thr1"])
+    eq(oracle.threshold2(x, 0.2, 1.4, 0.0, 1.0), golden["thr2_up"])
+    eq(oracle.threshold2(x, 1.4, 0.2, -1.0, 2.0), golden["thr2_down"])
+    eq(oracle.threshold4(x, -1.0, -0.5, 1.5, 2.0, 0.0, 1.0), golden["thr4"])
+    eq(oracle.threshold4(x, 2.0, 1.5, -0.5, -1.0, 0.0, 1.0), golden["thr4_rev"])
+    vol, mask = golden["vol"], golden["mask"]
+    ms = np.array([oracle.average(vol), oracle.stddev(vol), oracle.average(vol, mask), oracle.stddev(vol, mask)],
+                  np.float32)
+    eq(ms, golden["mean_std"])
+
+
+def test_blobs(oracle, golden):
+    bvol, sig = golden["blob_vol"], golden["blob_sigmas"]
+    mn, mx = oracle.blob_dog(bvol, sig, 0.02, 2.6482, minima_threshold=0.0, maxima_threshold=-np.inf,
+                             use_threshold_ratios=False)
+    eq(sort_blobs(mn), sort_blobs(golden["blob_minima"]))
+    eq(sort_blobs(mx), sort_blobs(golden["blob_maxima"]))
+    assert len(mn) > 0
+    mn, mx = oracle.blob_dog(bvol, sig, 0.02, 2.6482, minima_threshold=0.5, maxima_threshold=0.5,
+                             use_threshold_ratios=True)
+    eq(sort_blobs(mn), sort_blobs(golden["blob_minima_ratio"]))
+    eq(sort_blobs(mx), sort_blobs(golden["blob_maxima_ratio"]))
+
+
+def test_c1_reference_fixture(oracle, golden):
+    """BASELINE config 1: tests/test_membrane_detection.sh on test_image_membrane.rec, as run
+    by the stock filter_mrc binary (SURVEY.md 8c known answers)."""
+    if "c1_out" not in golden.files:
+        pytest.skip("C1 fixture not generated")
+    sigma, ratio, tv_sigma, expo, tv_ratio, frac = [float(v) for v in golden["c1_params"]]
+    m = oracle.membrane(golden["c1_in_binned"], sigma, ratio, 1, frac, True, tv_sigma, int(expo), tv_ratio)
+    eq(m["out"], golden["c1_out"])
+    c1 = golden["c1_out"]
+    assert abs(c1.sum(dtype=np.float64) / 4.141152e11 - 1) < 1e-6
+    assert abs(c1.max() / 6.827661e9 - 1) < 1e-6 and np.unravel_index(c1.argmax(), c1.shape) == (2, 3, 2)
+    assert (c1 != 0).sum() == 419
+    m0 = oracle.membrane(golden["c1_in_binned"], sigma, ratio, 1, frac, True, 0.0, int(expo), tv_ratio)
+    eq(m0["out"], golden["c1_out_notv"])
+    assert (m0["out"] != 0).sum() == 27
+
+
+def test_port_matches_reference_live(oracle, ref_oracle):
+    """Where oracle/_ref exists: fresh seeded inputs, every stage, bit for bit."""
+    from visfd_b200 import synth
+    vol = synth.tomogram((15, 18, 21), seed=11)
+    rng = np.random.default_rng(2)
+    mask = (rng.random(vol.shape) > 0.2).astype(np.float32)
+    for kw in (dict(), dict(mask=mask), dict(normalize=False)):
+        eq(oracle.apply_gauss(vol, 1.7, 4, **kw)[0], ref_oracle.apply_gauss(vol, 1.7, 4, **kw)[0])
+    eq(oracle.apply_log(vol, 2.0, 0.02, 2.6482)[0], ref_oracle.apply_log(vol, 2.0, 0.02, 2.6482)[0])
+    a = oracle.membrane(vol, 1.2, 2.6482, 1, 0.1, True, 3.0, 4, SQ2, mask=mask)
+    b = ref_oracle.membrane(vol, 1.2, 2.6482, 1, 0.1, True, 3.0, 4, SQ2, mask=mask)
+    for k in ("hess_saliency", "direction", "tensor", "out"):
+        eq(a[k], b[k])
+    assert a["threshold"] == b["threshold"]

@@ -1,0 +1,55 @@
+"""Parity metrics shared by the tests (tolerances from BASELINE.json:north_star)."""
+import numpy as np
+
+TOL_GAUSS = 1e-5      # Gaussian / DoG / LoG outputs
+TOL_SALIENCY = 1e-4   # ridge saliency, vote tensors, post-vote score
+
+
+def rel_err(a, b, floor_frac=1e-3):
+    """max |a-b| / max(|b|, floor) with floor = floor_frac * max|b| over the volume.
+
+    A per-voxel relative error with a floor: voxels whose reference value is a
+    cancellation residue (e.g. a Gaussian-blurred noise value near a zero crossing, or
+    lambda1^2 ~ lambda2^2) are judged against the scale of the volume instead of
+    their own ~0 magnitude."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    scale = np.abs(b).max() if b.size else 0.0
+    if scale == 0.0:
+        return float(np.abs(a).max()) if a.size else 0.0
+    den = np.maximum(np.abs(b), floor_frac * scale)
+    return float((np.abs(a - b) / den).max())
+
+
+def tensor_rel_err(a, b):
+    """Per-voxel Frobenius error of 6-component tensors relative to the tensor norm
+    (off-diagonal components cancel, so they are judged against the whole tensor)."""
+    a = np.asarray(a, np.float64).reshape(-1, 6)
+    b = np.asarray(b, np.float64).reshape(-1, 6)
+    w = np.array([1, 1, 1, 2, 2, 2], np.float64)
+    nb = np.sqrt((b * b * w).sum(1))
+    d = np.sqrt(((a - b) ** 2 * w).sum(1))
+    scale = nb.max() if nb.size else 0.0
+    if scale == 0.0:
+        return float(d.max()) if d.size else 0.0
+    return float((d / np.maximum(nb, 1e-3 * scale)).max())
+
+
+def direction_err(a, b, weight=None):
+    """max over voxels of 1 - |cos| between unit vectors (normals are sign-free)."""
+    a = np.asarray(a, np.float64).reshape(-1, 3)
+    b = np.asarray(b, np.float64).reshape(-1, 3)
+    c = np.abs((a * b).sum(1)) / np.maximum(np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1), 1e-30)
+    e = 1.0 - c
+    if weight is not None:
+        e = e[np.asarray(weight).reshape(-1) != 0]
+    return float(e.max()) if e.size else 0.0
+
+
+def sort_blobs(t):
+    """canonical order: (sigma, z, y, x)"""
+    t = np.asarray(t)
+    if len(t) == 0:
+        return t.reshape(0, 5)
+    idx = np.lexsort((t[:, 0], t[:, 1], t[:, 2], t[:, 3]))
+    return t[idx]

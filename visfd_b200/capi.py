@@ -1,0 +1,390 @@
+"""ctypes binding of the C ABI in include/visfd_cuda.h (visfd_b200/libvisfd_cuda.so).
+
+This is plumbing for tests, bench.py and the multi-GPU slab driver: every array may be
+a C-contiguous float32 numpy array (HOST path: the library stages it through device
+memory, exactly what the reference-side C++ shim does with Alloc3D memory) or a
+contiguous float32 torch CUDA tensor (DEVICE path: no copies).  Volumes are indexed
+[z][y][x] like the reference's ``aaafI[iz][iy][ix]``.
+
+There is no CPU fallback: importing works without a GPU (so that the symbol table can
+be checked), creating a Context without a usable B200 raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvisfd_cuda.so")
+
+INCREASING_EIVALS = 0
+DECREASING_EIVALS = 1
+SCORE_PLANAR = 0
+SCORE_LINEAR = 1
+THRESH_SINGLE, THRESH_2, THRESH_4, THRESH_GAUSS, RESCALE = 1, 2, 4, 5, 6
+
+_f, _i, _i64, _p, _d = C.c_float, C.c_int, C.c_int64, C.c_void_p, C.c_double
+
+
+class VisfdCudaError(RuntimeError):
+    """Mirror of VisfdErr (lib/visfd/err_visfd.hpp:15-22) for the Python host side."""
+
+
+class MembraneParams(C.Structure):
+    _fields_ = [("sigma", _f), ("truncate_ratio", _f), ("eival_order", _i), ("cut", _f),
+                ("cut_is_fraction", _i), ("tv_sigma", _f), ("tv_exponent", _i),
+                ("tv_cutoff_ratio", _f)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VisfdCudaError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C visfd_b200/csrc). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.visfd_cuda_last_error.restype = C.c_char_p
+    lib.visfd_cuda_launch_count.restype = _i64
+    lib.visfd_cuda_last_voter_count.restype = _i64
+    lib.visfd_cuda_stage_ms.restype = _d
+    lib.visfd_cuda_key_to_float.restype = _f
+    lib.visfd_cuda_set_timing.restype = None
+    lib.visfd_cuda_destroy.restype = None
+    lib.visfd_cuda_gen_gauss1d.restype = None
+    _lib = lib
+    return lib
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        assert x.is_cuda and x.is_contiguous() and x.dtype.is_floating_point and x.element_size() == 4
+        return _p(x.data_ptr())
+    assert isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous
+    return _p(x.ctypes.data)
+
+
+def _prep(x):
+    """float32, contiguous; numpy stays numpy, torch stays torch."""
+    if x is None:
+        return None
+    if _is_torch(x):
+        import torch
+        if not x.is_cuda:
+            raise VisfdCudaError("torch tensors must live on the GPU (use numpy for host arrays)")
+        return x.contiguous().to(torch.float32)
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def _empty(like, shape):
+    if _is_torch(like):
+        import torch
+        return torch.empty(shape, dtype=torch.float32, device=like.device)
+    return np.empty(shape, np.float32)
+
+
+def _zeros(like, shape):
+    if _is_torch(like):
+        import torch
+        return torch.zeros(shape, dtype=torch.float32, device=like.device)
+    return np.zeros(shape, np.float32)
+
+
+def _f3(v):
+    v = [v] * 3 if np.isscalar(v) else list(v)
+    return (_f * 3)(*v)
+
+
+def _i3(v):
+    v = [v] * 3 if np.isscalar(v) else list(v)
+    return (_i * 3)(*[int(t) for t in v])
+
+
+def gen_gauss1d(sigma, hw):
+    """GenFilterGauss1D<float>(sigma, hw) (lib/visfd/filter1d.hpp:411-460); host only."""
+    t = np.zeros(2 * hw + 1, np.float32)
+    load_library().visfd_cuda_gen_gauss1d(_f(sigma), _i(hw), _ptr(t))
+    return t
+
+
+def gauss_halfwidth(sigma, truncate_ratio=-1.0, truncate_threshold=0.03):
+    return load_library().visfd_cuda_gauss_halfwidth(_f(sigma), _f(truncate_ratio), _f(truncate_threshold))
+
+
+def tv_halfwidth(sigma, cutoff_ratio):
+    return load_library().visfd_cuda_tv_halfwidth(_f(sigma), _f(cutoff_ratio))
+
+
+class Context:
+    """One context per GPU (visfd_cuda_init)."""
+
+    def __init__(self, device=-1, stream=None):
+        self.lib = load_library()
+        self.h = _p()
+        rc = self.lib.visfd_cuda_init(_i(device), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise VisfdCudaError(self.lib.visfd_cuda_last_error().decode())
+        if stream is not None:
+            self._ck(self.lib.visfd_cuda_set_stream(self.h, _p(stream)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.visfd_cuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise VisfdCudaError(self.lib.visfd_cuda_last_error().decode())
+
+    @staticmethod
+    def _dims(shape):
+        nz, ny, nx = shape
+        return _i64(nx), _i64(ny), _i64(nz)
+
+    # ---- bookkeeping -----------------------------------------------------------------
+    def launch_count(self):
+        return self.lib.visfd_cuda_launch_count(self.h)
+
+    def stage_ms(self, stage):
+        return self.lib.visfd_cuda_stage_ms(self.h, stage.encode())
+
+    def set_timing(self, enabled):
+        self.lib.visfd_cuda_set_timing(self.h, _i(int(enabled)))
+
+    def trim(self):
+        self._ck(self.lib.visfd_cuda_trim(self.h))
+
+    def last_voter_count(self):
+        return self.lib.visfd_cuda_last_voter_count(self.h)
+
+    def fp32_peak(self, ms=200.0):
+        t = _d()
+        self._ck(self.lib.visfd_cuda_fp32_peak(self.h, _d(ms), C.byref(t)))
+        return t.value
+
+    def tv_count_pairs(self, saliency, threshold, halfwidth, mask_src=None, mask_dst=None):
+        s = _prep(saliency)
+        n = _i64()
+        self._ck(self.lib.visfd_cuda_tv_count_pairs(self.h, *self._dims(s.shape), _ptr(s), _f(threshold),
+                                                    _ptr(_prep(mask_src)), _ptr(_prep(mask_dst)),
+                                                    _i(halfwidth), C.byref(n)))
+        return n.value
+
+    # ---- separable filters --------------------------------------------------------------
+    def apply_separable(self, src, taps, mask=None, normalize=True):
+        """ApplySeparable (lib/visfd/filter3d.hpp:688-1050); taps = (tx, ty, tz) numpy arrays."""
+        src, mask = _prep(src), _prep(mask)
+        dst = _empty(src, src.shape)
+        t = [np.ascontiguousarray(a, np.float32) for a in taps]
+        hw = _i3([(len(a) - 1) // 2 for a in t])
+        tp = (_p * 3)(*[a.ctypes.data for a in t])
+        A = _f()
+        self._ck(self.lib.visfd_cuda_apply_separable(self.h, *self._dims(src.shape), _ptr(src), _ptr(dst),
+                                                     _ptr(mask), tp, hw, _i(int(normalize)), C.byref(A)))
+        return dst, A.value
+
+    def apply_gauss(self, src, sigma, hw, mask=None, normalize=True, z_offset=0, nz_global=None):
+        """ApplyGauss (lib/visfd/filter3d.hpp:1088-1124); slab form when z_offset/nz_global are given."""
+        src, mask = _prep(src), _prep(mask)
+        dst = _empty(src, src.shape)
+        A = _f()
+        nzg = src.shape[0] if nz_global is None else nz_global
+        self._ck(self.lib.visfd_cuda_apply_gauss_slab(self.h, *self._dims(src.shape), _i64(z_offset), _i64(nzg),
+                                                      _ptr(src), _ptr(dst), _ptr(mask), _f3(sigma), _i3(hw),
+                                                      _i(int(normalize)), C.byref(A)))
+        return dst, A.value
+
+    def apply_dog(self, src, sigma_a, sigma_b, hw, mask=None):
+        """ApplyDog (lib/visfd/filter3d.hpp:1340-1402)."""
+        src, mask = _prep(src), _prep(mask)
+        dst = _empty(src, src.shape)
+        A, B = _f(), _f()
+        self._ck(self.lib.visfd_cuda_apply_dog(self.h, *self._dims(src.shape), _ptr(src), _ptr(dst), _ptr(mask),
+                                               _f3(sigma_a), _f3(sigma_b), _i3(hw), C.byref(A), C.byref(B)))
+        return dst, A.value, B.value
+
+    def apply_log(self, src, sigma, delta=0.02, truncate_ratio=2.5, mask=None, z_offset=0, nz_global=None):
+        """ApplyLog (lib/visfd/filter3d.hpp:1430-1507)."""
+        src, mask = _prep(src), _prep(mask)
+        dst = _empty(src, src.shape)
+        A, B = _f(), _f()
+        nzg = src.shape[0] if nz_global is None else nz_global
+        self._ck(self.lib.visfd_cuda_apply_log_slab(self.h, *self._dims(src.shape), _i64(z_offset), _i64(nzg),
+                                                    _ptr(src), _ptr(dst), _ptr(mask), _f3(sigma), _f(delta),
+                                                    _f(truncate_ratio), C.byref(A), C.byref(B)))
+        return dst, A.value, B.value
+
+    # ---- Hessian / eigen --------------------------------------------------------------------
+    def calc_hessian(self, src, sigma, truncate_ratio, mask=None):
+        """CalcHessian (lib/visfd/feature.hpp:1210-1348) -> (gradient[...,3], hessian[...,6])."""
+        src, mask = _prep(src), _prep(mask)
+        grad = _zeros(src, tuple(src.shape) + (3,))
+        hess = _zeros(src, tuple(src.shape) + (6,))
+        self._ck(self.lib.visfd_cuda_calc_hessian(self.h, *self._dims(src.shape), _ptr(src), _ptr(mask), _f(sigma),
+                                                  _f(truncate_ratio), _ptr(grad), _ptr(hess)))
+        return grad, hess
+
+    def hessian_ridge(self, src, sigma, truncate_ratio, order=DECREASING_EIVALS, score_kind=SCORE_PLANAR,
+                      mask=None, want_direction=True):
+        """CalcHessian + the eigen/score loop of HandleTV (handlers.cpp:1645-1746), fused."""
+        src, mask = _prep(src), _prep(mask)
+        sal = _empty(src, src.shape)
+        dire = _zeros(src, tuple(src.shape) + (3,)) if want_direction else None
+        self._ck(self.lib.visfd_cuda_hessian_ridge(self.h, *self._dims(src.shape), _ptr(src), _ptr(mask), _f(sigma),
+                                                   _f(truncate_ratio), _i(order), _i(score_kind), _ptr(sal),
+                                                   _ptr(dire)))
+        return sal, dire
+
+    def tensor_score(self, tensor, order=DECREASING_EIVALS, score_kind=SCORE_PLANAR, is_vote_tensor=True,
+                     mask=None, out=None, want_eivals=False, want_direction=False):
+        tensor, mask = _prep(tensor), _prep(mask)
+        shape = tuple(tensor.shape[:-1])
+        n = int(np.prod(shape))
+        score = _zeros(tensor, shape) if out is None else _prep(out)
+        ev = _zeros(tensor, shape + (3,)) if want_eivals else None
+        dr = _zeros(tensor, shape + (3,)) if want_direction else None
+        self._ck(self.lib.visfd_cuda_tensor_score(self.h, _i64(n), _ptr(tensor), _ptr(mask), _i(order),
+                                                  _i(score_kind), _i(int(is_vote_tensor)), _ptr(score), _ptr(ev),
+                                                  _ptr(dr)))
+        return score, ev, dr
+
+    # ---- saliency cut ----------------------------------------------------------------------------
+    def saliency_cut(self, sal, cut, is_fraction, mask=None):
+        """handlers.cpp:1751-1797 -> (saliency after the cut, threshold)."""
+        mask = _prep(mask)
+        if _is_torch(sal):
+            out = _prep(sal).clone()
+        else:
+            out = np.array(sal, dtype=np.float32, copy=True, order="C")
+        thr = _f()
+        self._ck(self.lib.visfd_cuda_saliency_cut(self.h, _i64(out.size if not _is_torch(out) else out.numel()),
+                                                  _ptr(out), _ptr(mask), _f(cut), _i(int(is_fraction)),
+                                                  C.byref(thr)))
+        return out, thr.value
+
+    def select_hist(self, sal, prefix, prefix_bits, mask=None):
+        sal, mask = _prep(sal), _prep(mask)
+        n = sal.numel() if _is_torch(sal) else sal.size
+        hist = np.zeros(2048, np.uint64)
+        self._ck(self.lib.visfd_cuda_select_hist(self.h, _i64(n), _ptr(sal), _ptr(mask), C.c_uint32(prefix),
+                                                 _i(prefix_bits), hist.ctypes.data_as(_p)))
+        return hist
+
+    def select_step(self, hist, prefix, prefix_bits, rank):
+        hist = np.ascontiguousarray(hist, np.uint64)
+        p, b, r = C.c_uint32(prefix), _i(prefix_bits), C.c_uint64(rank)
+        rc = self.lib.visfd_cuda_select_step(hist.ctypes.data_as(_p), C.byref(p), C.byref(b), C.byref(r))
+        if rc != 0:
+            raise VisfdCudaError("saliency cut: rank outside the population")
+        return p.value, b.value, r.value
+
+    def key_to_float(self, key):
+        return self.lib.visfd_cuda_key_to_float(C.c_uint32(key))
+
+    # ---- tensor voting -------------------------------------------------------------------------------
+    def tv_dense_stick(self, sal, direction, sigma, exponent, cutoff_ratio, mask_src=None, mask_dst=None,
+                       curves=False):
+        """TV3D(sigma, exponent, cutoff_ratio).TVDenseStick (lib/visfd/feature.hpp:1712-2037)."""
+        sal, direction = _prep(sal), _prep(direction)
+        tensor = _zeros(sal, tuple(sal.shape) + (6,))
+        self._ck(self.lib.visfd_cuda_tv_dense_stick(self.h, *self._dims(sal.shape), _ptr(sal), _ptr(direction),
+                                                    _ptr(_prep(mask_src)), _ptr(_prep(mask_dst)), _f(sigma),
+                                                    _i(exponent), _f(cutoff_ratio), _i(int(curves)), _i(0), _i(0),
+                                                    _ptr(tensor)))
+        return tensor
+
+    def membrane(self, src, sigma, truncate_ratio, order, cut, cut_is_fraction, tv_sigma, tv_exponent,
+                 tv_cutoff_ratio, mask=None, want_saliency=False, want_direction=False, want_tensor=False,
+                 out=None):
+        """The fused HandleTV pipeline (bin/filter_mrc/handlers.cpp:1618-1892)."""
+        src, mask = _prep(src), _prep(mask)
+        p = MembraneParams(sigma, truncate_ratio, order, cut, int(cut_is_fraction), tv_sigma, tv_exponent,
+                           tv_cutoff_ratio)
+        res = out if out is not None else _empty(src, src.shape)
+        sal = _empty(src, src.shape) if want_saliency else None
+        dire = _zeros(src, tuple(src.shape) + (3,)) if want_direction else None
+        tensor = _empty(src, tuple(src.shape) + (6,)) if want_tensor else None
+        thr = _f()
+        self._ck(self.lib.visfd_cuda_membrane(self.h, *self._dims(src.shape), _ptr(src), _ptr(mask), C.byref(p),
+                                              _ptr(res), _ptr(sal), _ptr(dire), _ptr(tensor), C.byref(thr)))
+        return dict(out=res, hess_saliency=sal, direction=dire, tensor=tensor, threshold=thr.value)
+
+    # ---- slab stages (device tensors only) -----------------------------------------------------------------
+    def ridge_saliency_slab(self, src, z_offset, nz_global, sigma, truncate_ratio, order=DECREASING_EIVALS,
+                            score_kind=SCORE_PLANAR, mask=None, smoothed=None, saliency=None):
+        src, mask = _prep(src), _prep(mask)
+        smoothed = _empty(src, src.shape) if smoothed is None else smoothed
+        saliency = _empty(src, src.shape) if saliency is None else saliency
+        self._ck(self.lib.visfd_cuda_ridge_saliency_slab(self.h, *self._dims(src.shape), _i64(z_offset),
+                                                         _i64(nz_global), _ptr(src), _ptr(mask), _f(sigma),
+                                                         _f(truncate_ratio), _i(order), _i(score_kind),
+                                                         _ptr(smoothed), _ptr(saliency)))
+        return smoothed, saliency
+
+    def vote_slab(self, saliency, smoothed, z_offset, nz_global, own, vote, threshold, params, mask=None,
+                  want_tensor=False, out=None):
+        shape = tuple(saliency.shape)
+        n_own = own[1] - own[0]
+        res = out if out is not None else _empty(saliency, (n_own,) + shape[1:])
+        tensor = _empty(saliency, (n_own,) + shape[1:] + (6,)) if want_tensor else None
+        self._ck(self.lib.visfd_cuda_vote_slab(self.h, *self._dims(shape), _i64(z_offset), _i64(nz_global),
+                                               _i64(own[0]), _i64(own[1]), _i64(vote[0]), _i64(vote[1]),
+                                               _ptr(saliency), _ptr(smoothed), _ptr(_prep(mask)), _f(threshold),
+                                               C.byref(params), _ptr(res), _ptr(tensor)))
+        return res, tensor
+
+    # ---- thresholds -----------------------------------------------------------------------------------------------
+    def threshold(self, a, kind, t, outA=0.0, outB=1.0, mask=None, masked_value=None, out=None):
+        """HandleThresholds inner loop (handlers.cpp:1037-1080) + mask fill (filter_mrc.cpp:771-776)."""
+        a, mask = _prep(a), _prep(mask)
+        res = _empty(a, a.shape) if out is None else _prep(out)
+        t4 = (_f * 4)(*(list(t) + [0.0] * (4 - len(t))))
+        n = res.numel() if _is_torch(res) else res.size
+        self._ck(self.lib.visfd_cuda_threshold(self.h, _i64(n), _ptr(a), _ptr(res), _i(kind), t4, _f(outA), _f(outB),
+                                               _ptr(mask), _i(int(masked_value is not None)),
+                                               _f(0.0 if masked_value is None else masked_value)))
+        return res
+
+    def mean_stddev(self, a, weights=None):
+        a, weights = _prep(a), _prep(weights)
+        n = a.numel() if _is_torch(a) else a.size
+        m, s = _f(), _f()
+        self._ck(self.lib.visfd_cuda_mean_stddev(self.h, _i64(n), _ptr(a), _ptr(weights), C.byref(m), C.byref(s)))
+        return m.value, s.value
+
+    # ---- blobs -----------------------------------------------------------------------------------------------------
+    def blob_dog(self, src, sigmas, delta=0.02, truncate_ratio=2.5, mask=None, minima_threshold=np.inf,
+                 maxima_threshold=-np.inf, use_threshold_ratios=True, capacity=1 << 20):
+        """BlobDog (lib/visfd/feature.hpp:56-427) -> (minima, maxima) rows of x,y,z,sigma,score."""
+        src, mask = _prep(src), _prep(mask)
+        sg = np.ascontiguousarray(np.asarray(sigmas), np.float32)
+        bufs = [np.zeros((capacity, 3), np.float32), np.zeros(capacity, np.float32), np.zeros(capacity, np.float32),
+                np.zeros((capacity, 3), np.float32), np.zeros(capacity, np.float32), np.zeros(capacity, np.float32)]
+        nmin, nmax = _i64(), _i64()
+        self._ck(self.lib.visfd_cuda_blob_dog(self.h, *self._dims(src.shape), _ptr(src), _ptr(mask), _ptr(sg),
+                                              _i(len(sg)), _f(delta), _f(truncate_ratio), _f(minima_threshold),
+                                              _f(maxima_threshold), _i(int(use_threshold_ratios)), _i64(capacity),
+                                              _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]), C.byref(nmin),
+                                              _ptr(bufs[3]), _ptr(bufs[4]), _ptr(bufs[5]), C.byref(nmax)))
+        a, b = min(nmin.value, capacity), min(nmax.value, capacity)
+
+        def pack(c, s, sc, n):
+            return np.concatenate([c[:n], s[:n, None], sc[:n, None]], axis=1)
+        return pack(bufs[0], bufs[1], bufs[2], a), pack(bufs[3], bufs[4], bufs[5], b)

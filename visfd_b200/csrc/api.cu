@@ -1,0 +1,432 @@
+// api.cu -- the extern "C" entry points declared in include/visfd_cuda.h: argument
+// checks, host<->device staging for the drop-in (host pointer) path, error mapping.
+// All compute is in the other translation units; nothing here runs on the CPU except
+// parameter generation (taps, half-widths), which the reference also does on the host.
+#include "common.cuh"
+#include "kernels.cuh"
+#include <cmath>
+#include <algorithm>
+
+using namespace visfd_cuda;
+
+#define API_BEGIN(ctx)                                         \
+  try {                                                        \
+    VREQUIRE((ctx) != nullptr, "context is NULL");             \
+    VCK(cudaSetDevice((ctx)->device));                         \
+    reset_stage_times(ctx);
+
+#define API_END(ctx)                                           \
+    VCK(cudaStreamSynchronize((ctx)->stream));                 \
+    resolve_stage_times(ctx);                                  \
+    return 0;                                                  \
+  } catch (const std::exception &ex) {                         \
+    set_last_error(ex.what());                                 \
+    if (ctx) { cudaStreamSynchronize((ctx)->stream); cudaGetLastError(); } \
+    return 1;                                                  \
+  }
+
+static void check_dims(int64_t nx, int64_t ny, int64_t nz) {
+  VREQUIRE(nx > 0 && ny > 0 && nz > 0, "image dimensions must be positive");
+  VREQUIRE(nx < (1LL << 31) && ny < (1LL << 31) && nz < (1LL << 31), "image dimension too large");
+}
+
+static bool on_host(const void *p) { return p != nullptr && !is_device_pointer(p); }
+
+extern "C" {
+
+// ---- host-side parameter helpers ---------------------------------------------------------
+void visfd_cuda_gen_gauss1d(float sigma, int hw, float *taps) { gen_gauss1d(sigma, hw, taps); }
+
+int visfd_cuda_gauss_halfwidth(float sigma, float truncate_ratio, float truncate_threshold) {
+  // bin/filter_mrc/filter3d_variants.hpp:516-518, lib/visfd/filter3d.hpp:1241-1246
+  if (truncate_ratio <= 0) truncate_ratio = sqrtf(-2 * logf(truncate_threshold));  // float overloads, as in the reference
+  int hw = (int)floorf(sigma * truncate_ratio);
+  if (hw < 1) hw = 1;
+  return hw;
+}
+
+int visfd_cuda_tv_halfwidth(float sigma, float cutoff_ratio) { return tv_halfwidth(sigma, cutoff_ratio); }
+
+// ---- separable filters ---------------------------------------------------------------------
+int visfd_cuda_apply_separable(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src,
+                               float *dst, const float *mask, const float *const taps[3],
+                               const int hw[3], int normalize, float *A_out) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz);
+  VREQUIRE(src && dst && taps && hw, "NULL argument");
+  const size_t N = (size_t)nx * ny * nz;
+  const bool host = on_host(src);
+  Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host), d(ctx, dst, N, Dir::Out, host);
+  float A = separable_device(ctx, nx, ny, nz, 0, nz, s.get(), d.get(), m.get(), taps, hw, normalize != 0,
+                             nullptr, 1.0f);
+  d.finish();
+  if (A_out) *A_out = A;
+  API_END(ctx)
+}
+
+int visfd_cuda_apply_gauss_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
+                                int64_t nz_global, const float *src, float *dst, const float *mask,
+                                const float sigma[3], const int hw[3], int normalize, float *A_out) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz_local);
+  VREQUIRE(src && dst && sigma && hw, "NULL argument");
+  const size_t N = (size_t)nx * ny * nz_local;
+  const bool host = on_host(src);
+  Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host), d(ctx, dst, N, Dir::Out, host);
+  float A = gauss_device(ctx, nx, ny, nz_local, z_offset, nz_global, s.get(), d.get(), m.get(), sigma, hw,
+                         normalize != 0, nullptr, 1.0f);
+  d.finish();
+  if (A_out) *A_out = A;
+  API_END(ctx)
+}
+
+int visfd_cuda_apply_gauss(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src, float *dst,
+                           const float *mask, const float sigma[3], const int hw[3], int normalize,
+                           float *A_out) {
+  return visfd_cuda_apply_gauss_slab(ctx, nx, ny, nz, 0, nz, src, dst, mask, sigma, hw, normalize, A_out);
+}
+
+int visfd_cuda_apply_dog(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src, float *dst,
+                         const float *mask, const float sigma_a[3], const float sigma_b[3], const int hw[3],
+                         float *A_out, float *B_out) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz);
+  VREQUIRE(src && dst && sigma_a && sigma_b && hw, "NULL argument");
+  const size_t N = (size_t)nx * ny * nz;
+  const bool host = on_host(src);
+  Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host), d(ctx, dst, N, Dir::Out, host);
+  dog_device(ctx, nx, ny, nz, 0, nz, s.get(), d.get(), m.get(), sigma_a, sigma_b, hw, 1.0f, A_out, B_out);
+  d.finish();
+  API_END(ctx)
+}
+
+int visfd_cuda_apply_log_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
+                              int64_t nz_global, const float *src, float *dst, const float *mask,
+                              const float sigma[3], float delta, float truncate_ratio, float *A_out,
+                              float *B_out) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz_local);
+  VREQUIRE(src && dst && sigma, "NULL argument");
+  const size_t N = (size_t)nx * ny * nz_local;
+  const bool host = on_host(src);
+  float sa[3], sb[3], scale, A = 0, B = 0;
+  int hw[3];
+  log_params(sigma, delta, truncate_ratio, sa, sb, hw, &scale);
+  Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host), d(ctx, dst, N, Dir::Out, host);
+  dog_device(ctx, nx, ny, nz_local, z_offset, nz_global, s.get(), d.get(), m.get(), sa, sb, hw, scale, &A, &B);
+  d.finish();
+  // lib/visfd/filter3d.hpp:1500-1504: the reported peak heights are scaled as well
+  if (A_out) *A_out = A * scale;
+  if (B_out) *B_out = B * scale;
+  API_END(ctx)
+}
+
+int visfd_cuda_apply_log(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src, float *dst,
+                         const float *mask, const float sigma[3], float delta, float truncate_ratio,
+                         float *A_out, float *B_out) {
+  return visfd_cuda_apply_log_slab(ctx, nx, ny, nz, 0, nz, src, dst, mask, sigma, delta, truncate_ratio,
+                                   A_out, B_out);
+}
+
+// ---- Hessian / eigen -------------------------------------------------------------------------
+static void smooth_for_hessian(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
+                               int64_t nz_global, const float *src, const float *mask, float sigma,
+                               float truncate_ratio, float *smoothed) {
+  // CalcHessian, lib/visfd/feature.hpp:1223, :1248-1255: hw = floor(sigma*ratio), normalised
+  int h = (int)floor(sigma * truncate_ratio);
+  VREQUIRE(h >= 0, "negative Gaussian half-width");
+  float sg[3] = {sigma, sigma, sigma};
+  int hw[3] = {h, h, h};
+  gauss_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, smoothed, mask, sg, hw, true, nullptr, 1.0f);
+}
+
+int visfd_cuda_calc_hessian(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src,
+                            const float *mask, float sigma, float truncate_ratio, float *gradient,
+                            float *hessian) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz);
+  VREQUIRE(src && (gradient || hessian), "NULL argument");
+  const size_t N = (size_t)nx * ny * nz;
+  const bool host = on_host(src);
+  Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host);
+  // entries of masked voxels are left untouched => outputs are read-modify-write when masked
+  Dir od = mask ? Dir::InOut : Dir::Out;
+  Staged<float> g(ctx, gradient, 3 * N, od, host), h(ctx, hessian, 6 * N, od, host);
+  Scratch<float> sm(ctx, N);
+  smooth_for_hessian(ctx, nx, ny, nz, 0, nz, s.get(), m.get(), sigma, truncate_ratio, sm.get());
+  hessian_fd_device(ctx, nx, ny, nz, 0, nz, sm.get(), m.get(), sigma, g.get(), h.get());
+  g.finish();
+  h.finish();
+  API_END(ctx)
+}
+
+int visfd_cuda_hessian_ridge(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src,
+                             const float *mask, float sigma, float truncate_ratio, int eival_order,
+                             int score_kind, float *saliency, float *direction) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz);
+  VREQUIRE(src && saliency, "NULL argument");
+  const size_t N = (size_t)nx * ny * nz;
+  const bool host = on_host(src);
+  Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host);
+  Staged<float> sal(ctx, saliency, N, Dir::Out, host);
+  Staged<float> dir(ctx, direction, 3 * N, mask ? Dir::InOut : Dir::Out, host);
+  Scratch<float> sm(ctx, N);
+  smooth_for_hessian(ctx, nx, ny, nz, 0, nz, s.get(), m.get(), sigma, truncate_ratio, sm.get());
+  ridge_device(ctx, nx, ny, nz, 0, nz, 0, nz, sm.get(), m.get(), sigma, eival_order, score_kind, sal.get(),
+               dir.get());
+  sal.finish();
+  dir.finish();
+  API_END(ctx)
+}
+
+int visfd_cuda_tensor_score(visfd_ctx *ctx, int64_t n, const float *tensor, const float *mask,
+                            int eival_order, int score_kind, int kind_is_vote_tensor, float *score,
+                            float *eivals, float *direction) {
+  API_BEGIN(ctx)
+  VREQUIRE(n >= 0 && tensor, "bad arguments");
+  const bool host = on_host(tensor);
+  Staged<float> t(ctx, tensor, 6 * (size_t)n, Dir::In, host), m(ctx, mask, n, Dir::In, host);
+  Dir od = mask ? Dir::InOut : Dir::Out;
+  Staged<float> sc(ctx, score, n, od, host), ev(ctx, eivals, 3 * (size_t)n, od, host),
+      dr(ctx, direction, 3 * (size_t)n, od, host);
+  tensor_score_device(ctx, n, t.get(), m.get(), eival_order, score_kind, kind_is_vote_tensor, sc.get(),
+                      ev.get(), dr.get());
+  sc.finish();
+  ev.finish();
+  dr.finish();
+  API_END(ctx)
+}
+
+// ---- saliency cut -------------------------------------------------------------------------------
+int visfd_cuda_saliency_cut(visfd_ctx *ctx, int64_t n, float *saliency, const float *mask, float cut,
+                            int is_fraction, float *threshold_out) {
+  API_BEGIN(ctx)
+  VREQUIRE(n > 0 && saliency, "bad arguments");
+  const bool host = on_host(saliency);
+  Staged<float> s(ctx, saliency, n, Dir::InOut, host), m(ctx, mask, n, Dir::In, host);
+  float thr = cut;
+  if (is_fraction) thr = select_threshold_device(ctx, n, s.get(), m.get(), cut);
+  apply_cut_device(ctx, n, s.get(), thr);
+  s.finish();
+  if (threshold_out) *threshold_out = thr;
+  API_END(ctx)
+}
+
+int visfd_cuda_select_hist(visfd_ctx *ctx, int64_t n, const float *saliency, const float *mask,
+                           uint32_t prefix, int prefix_bits, uint64_t *hist) {
+  API_BEGIN(ctx)
+  VREQUIRE(n >= 0 && hist && (n == 0 || saliency), "bad arguments");
+  const bool host = on_host(saliency);
+  Staged<float> s(ctx, saliency, n, Dir::In, host), m(ctx, mask, n, Dir::In, host);
+  select_hist_device(ctx, n, s.get(), m.get(), prefix, prefix_bits, hist);
+  API_END(ctx)
+}
+
+int visfd_cuda_select_step(const uint64_t *hist, uint32_t *prefix, int *prefix_bits, uint64_t *rank) {
+  if (!hist || !prefix || !prefix_bits || !rank) return 1;
+  return select_step_host(hist, prefix, prefix_bits, rank);
+}
+
+float visfd_cuda_key_to_float(uint32_t key) { return key_to_float(key); }
+
+// ---- tensor voting -------------------------------------------------------------------------------
+int visfd_cuda_tv_dense_stick(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *saliency,
+                              const float *direction, const float *mask_src, const float *mask_dst,
+                              float sigma, int exponent, float cutoff_ratio, int curves, int normalize,
+                              int diagonalize_dest, float *tensor) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz);
+  VREQUIRE(saliency && direction && tensor, "NULL argument");
+  VREQUIRE(!normalize && !diagonalize_dest,
+           "TVDenseStick: normalize / diagonalize_dest are not supported (filter_mrc passes false for both)");
+  const size_t N = (size_t)nx * ny * nz;
+  const bool host = on_host(saliency);
+  Staged<float> s(ctx, saliency, N, Dir::In, host), d(ctx, direction, 3 * N, Dir::In, host),
+      ms(ctx, mask_src, N, Dir::In, host), md(ctx, mask_dst, N, Dir::In, host),
+      t(ctx, tensor, 6 * N, Dir::Out, host);
+  TVParams p{sigma, exponent, cutoff_ratio, curves};
+  tv_device(ctx, nx, ny, nz, 0, nz, 0, nz, s.get(), -INFINITY, d.get(), nullptr, 0.0f, 0, 0, ms.get(),
+            md.get(), p, t.get(), nullptr);
+  t.finish();
+  API_END(ctx)
+}
+
+// ---- fused membrane pipeline ------------------------------------------------------------------------
+int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src,
+                        const float *mask, const visfd_membrane_params *p, float *out,
+                        float *hess_saliency, float *direction, float *tensor, float *threshold_out) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz);
+  VREQUIRE(src && p && out, "NULL argument");
+  const size_t N = (size_t)nx * ny * nz;
+  const bool host = on_host(src);
+  Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host);
+  Staged<float> o(ctx, out, N, Dir::Out, host);
+  Staged<float> hs(ctx, hess_saliency, N, Dir::Out, host);
+  Staged<float> dir(ctx, direction, 3 * N, mask ? Dir::InOut : Dir::Out, host);
+  Staged<float> tn(ctx, tensor, 6 * N, Dir::Out, host);
+  const bool vote = p->tv_sigma > 0.0f;
+
+  Scratch<float> sm(ctx, N);
+  smooth_for_hessian(ctx, nx, ny, nz, 0, nz, s.get(), m.get(), p->sigma, p->truncate_ratio, sm.get());
+  // saliency lives in `out` when there is no voting, else in hess_saliency's buffer or scratch
+  Scratch<float> sal_scratch;
+  float *sal = nullptr;
+  if (!vote) sal = o.get();
+  else if (hs.get()) sal = hs.get();
+  else { sal_scratch.reset(ctx, N); sal = sal_scratch.get(); }
+  ridge_device(ctx, nx, ny, nz, 0, nz, 0, nz, sm.get(), m.get(), p->sigma, p->eival_order,
+               VISFD_SCORE_PLANAR, sal, dir.get());
+  float thr = p->cut;
+  if (p->cut_is_fraction) thr = select_threshold_device(ctx, N, sal, m.get(), p->cut);
+  if (threshold_out) *threshold_out = thr;
+  if (vote) {
+    TVParams tp{p->tv_sigma, p->tv_exponent, p->tv_cutoff_ratio, 0};
+    // voters' directions: the stored field if the caller asked for it, else recomputed
+    // for the surviving ~5 % only
+    tv_device(ctx, nx, ny, nz, 0, nz, 0, nz, sal, thr, dir.get(), sm.get(), p->sigma, p->eival_order,
+              VISFD_SCORE_PLANAR, m.get(), m.get(), tp, tn.get(), o.get());
+    if (hs.get()) apply_cut_device(ctx, N, hs.get(), thr);
+  } else {
+    apply_cut_device(ctx, N, sal, thr);
+    if (hs.get()) VCK(cudaMemcpyAsync(hs.get(), sal, N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    VREQUIRE(!tensor, "tensor output requested without voting");
+  }
+  o.finish();
+  hs.finish();
+  dir.finish();
+  tn.finish();
+  API_END(ctx)
+}
+
+int visfd_cuda_ridge_saliency_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
+                                   int64_t nz_global, const float *src, const float *mask, float sigma,
+                                   float truncate_ratio, int eival_order, int score_kind, float *smoothed,
+                                   float *saliency) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz_local);
+  VREQUIRE(src && smoothed && saliency, "NULL argument");
+  VREQUIRE(is_device_pointer(src) && is_device_pointer(smoothed) && is_device_pointer(saliency) &&
+               (!mask || is_device_pointer(mask)),
+           "slab entry points take device pointers only");
+  smooth_for_hessian(ctx, nx, ny, nz_local, z_offset, nz_global, src, mask, sigma, truncate_ratio, smoothed);
+  // planes whose +-1 neighbours exist in the slab (or are clamped at the global border)
+  int64_t z0 = (z_offset == 0) ? 0 : 1;
+  int64_t z1 = (z_offset + nz_local == nz_global) ? nz_local : nz_local - 1;
+  const size_t plane = (size_t)nx * ny;
+  if (z0 > 0) VCK(cudaMemsetAsync(saliency, 0, plane * sizeof(float), ctx->stream));
+  if (z1 < nz_local) VCK(cudaMemsetAsync(saliency + (size_t)z1 * plane, 0, plane * sizeof(float), ctx->stream));
+  if (z1 > z0)
+    ridge_device(ctx, nx, ny, nz_local, z_offset, nz_global, z0, z1, smoothed, mask, sigma, eival_order,
+                 score_kind, saliency, nullptr);
+  API_END(ctx)
+}
+
+int visfd_cuda_vote_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
+                         int64_t nz_global, int64_t own_z0, int64_t own_z1, int64_t vote_z0, int64_t vote_z1,
+                         const float *saliency, const float *smoothed, const float *mask, float threshold,
+                         const visfd_membrane_params *p, float *out, float *tensor) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz_local);
+  VREQUIRE(saliency && smoothed && p && out, "NULL argument");
+  VREQUIRE(is_device_pointer(saliency) && is_device_pointer(smoothed) && is_device_pointer(out),
+           "slab entry points take device pointers only");
+  VREQUIRE(0 <= vote_z0 && vote_z0 <= own_z0 && own_z0 <= own_z1 && own_z1 <= vote_z1 && vote_z1 <= nz_local,
+           "plane ranges must nest: 0 <= vote_z0 <= own_z0 <= own_z1 <= vote_z1 <= nz_local");
+  const size_t plane = (size_t)nx * ny;
+  const size_t n_own = plane * (size_t)(own_z1 - own_z0);
+  if (p->tv_sigma > 0.0f) {
+    // direction recompute reads smoothed planes vote_z0-1 .. vote_z1 (clamped at the global border)
+    VREQUIRE((vote_z0 >= 1 || z_offset == 0) && (vote_z1 <= nz_local - 1 || z_offset + nz_local == nz_global),
+             "slab lacks the 1-plane halo around the voter planes");
+    TVParams tp{p->tv_sigma, p->tv_exponent, p->tv_cutoff_ratio, 0};
+    const size_t o = plane * (size_t)vote_z0;
+    tv_device(ctx, nx, ny, vote_z1 - vote_z0, z_offset + vote_z0, nz_global, own_z0 - vote_z0,
+              own_z1 - vote_z0, saliency + o, threshold, nullptr, smoothed + o, p->sigma, p->eival_order,
+              VISFD_SCORE_PLANAR, mask ? mask + o : nullptr, mask ? mask + o : nullptr, tp, tensor, out);
+  } else {
+    VCK(cudaMemcpyAsync(out, saliency + plane * (size_t)own_z0, n_own * sizeof(float), cudaMemcpyDeviceToDevice,
+                        ctx->stream));
+    apply_cut_device(ctx, n_own, out, threshold);
+  }
+  API_END(ctx)
+}
+
+// ---- threshold / mask maps --------------------------------------------------------------------------
+int visfd_cuda_threshold(visfd_ctx *ctx, int64_t n, const float *in, float *out, int kind, const float t[4],
+                         float outA, float outB, const float *mask, int use_masked_value, float masked_value) {
+  API_BEGIN(ctx)
+  VREQUIRE(n >= 0 && out && (in || kind == VISFD_RESCALE), "bad arguments");
+  const bool host = on_host(out);
+  Staged<float> i(ctx, in, n, Dir::In, host), m(ctx, mask, n, Dir::In, host);
+  Staged<float> o(ctx, out, n, kind == VISFD_RESCALE ? Dir::InOut : Dir::Out, host);
+  threshold_device(ctx, n, i.get(), o.get(), kind, t, outA, outB, m.get(), use_masked_value, masked_value);
+  o.finish();
+  API_END(ctx)
+}
+
+int visfd_cuda_mean_stddev(visfd_ctx *ctx, int64_t n, const float *in, const float *weights, float *mean_out,
+                           float *stddev_out) {
+  API_BEGIN(ctx)
+  VREQUIRE(n > 0 && in, "bad arguments");
+  const bool host = on_host(in);
+  Staged<float> i(ctx, in, n, Dir::In, host), w(ctx, weights, n, Dir::In, host);
+  mean_stddev_device(ctx, n, i.get(), w.get(), mean_out, stddev_out);
+  API_END(ctx)
+}
+
+// ---- blob detection ------------------------------------------------------------------------------------
+int visfd_cuda_blob_dog(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src, const float *mask,
+                        const float *sigmas, int n_sigmas, float delta, float truncate_ratio,
+                        float minima_threshold, float maxima_threshold, int use_threshold_ratios,
+                        int64_t capacity, float *min_crds, float *min_sigma, float *min_score,
+                        int64_t *n_minima, float *max_crds, float *max_sigma, float *max_score,
+                        int64_t *n_maxima) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz);
+  VREQUIRE(src && sigmas && n_sigmas >= 0 && capacity >= 0, "bad arguments");
+  const size_t N = (size_t)nx * ny * nz;
+  const bool host = on_host(src);
+  Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host);
+  BlobList mins, maxs;
+  blob_dog_device(ctx, nx, ny, nz, s.get(), m.get(), sigmas, n_sigmas, delta, truncate_ratio, minima_threshold,
+                  maxima_threshold, use_threshold_ratios, mins, maxs);
+  auto emit = [&](const BlobList &l, float *crds, float *sg, float *sc, int64_t *cnt) {
+    int64_t n = (int64_t)l.score.size();
+    if (cnt) *cnt = n;
+    int64_t k = std::min(n, capacity);
+    if (crds && k) memcpy(crds, l.crds.data(), 3 * k * sizeof(float));
+    if (sg && k) memcpy(sg, l.sigma.data(), k * sizeof(float));
+    if (sc && k) memcpy(sc, l.score.data(), k * sizeof(float));
+  };
+  emit(mins, min_crds, min_sigma, min_score, n_minima);
+  emit(maxs, max_crds, max_sigma, max_score, n_maxima);
+  API_END(ctx)
+}
+
+// ---- bookkeeping -------------------------------------------------------------------------------------------
+int64_t visfd_cuda_last_voter_count(visfd_ctx *ctx) { return ctx ? ctx->last_voters : -1; }
+
+int visfd_cuda_tv_count_pairs(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *saliency,
+                              float threshold, const float *mask_src, const float *mask_dst, int halfwidth,
+                              int64_t *pairs) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz);
+  VREQUIRE(saliency && pairs, "NULL argument");
+  const size_t N = (size_t)nx * ny * nz;
+  const bool host = on_host(saliency);
+  Staged<float> s(ctx, saliency, N, Dir::In, host), ms(ctx, mask_src, N, Dir::In, host),
+      md(ctx, mask_dst, N, Dir::In, host);
+  *pairs = tv_count_pairs_device(ctx, nx, ny, nz, s.get(), threshold, ms.get(), md.get(), halfwidth);
+  API_END(ctx)
+}
+
+int visfd_cuda_fp32_peak(visfd_ctx *ctx, double ms, double *tflops) {
+  API_BEGIN(ctx)
+  VREQUIRE(tflops, "NULL argument");
+  *tflops = fp32_peak_device(ctx, ms);
+  API_END(ctx)
+}
+
+}  // extern "C"

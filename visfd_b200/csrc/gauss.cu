@@ -1,0 +1,459 @@
+// gauss.cu -- separable 3-D filtering (ApplySeparable / ApplyGauss / ApplyDog / ApplyLog)
+// as three streaming sweeps Z -> Y -> X, the order of lib/visfd/filter3d.hpp:741-981.
+//
+// Data layout: dense float32 [nz][ny][nx], x fastest.  Every sweep reads 4 B and
+// writes 4 B per voxel (24 B/voxel per Gaussian); the un-masked normalisation
+// (filter3d.hpp:1004-1022) and the DoG / LoG combine (filter3d.hpp:1387-1390,
+// :1493-1498) are fused into the X sweep's epilogue, so they cost no extra pass.
+//
+// Kernels
+//  sweep_axis_kernel : Y or Z sweep.  Lanes run along x (float4 per lane, 512 B
+//      coalesced per warp row); a CTA stages (64 + 2hw) rows of 128 columns in
+//      shared memory once and every thread produces 8 consecutive outputs along
+//      the sweep axis for its 4 columns from registers (32 accumulators), so a
+//      shared-memory value is read once per thread and used for 8 FMAs x 4 lanes.
+//  sweep_x_kernel    : X sweep.  A CTA stages 32 row segments of 128 + 2hw columns;
+//      every thread produces 4 consecutive x outputs for 4 rows (16 accumulators),
+//      reading shared memory as conflict-free float4.
+// Out-of-volume taps are zero (the reference skips them, filter1d.hpp:98-99); the
+// renormalisation divides by the product of the three 1-D edge profiles.
+#include "common.cuh"
+#include "kernels.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace visfd_cuda {
+
+// ---------------------------------------------------------------------------------
+// host: taps
+// ---------------------------------------------------------------------------------
+// GenFilterGauss1D<float>: lib/visfd/filter1d.hpp:411-460.  Discrete Gaussian kernel
+// exp(-s^2) I_|i|(s^2) for s<=10 and |i|<=20, sampled continuous Gaussian otherwise,
+// in long double; stored as float; normalised by the long double sum of the floats.
+void gen_gauss1d(float sigma, int hw, float *taps) {
+  long double sum = 0.0L;
+  for (int i = -hw; i <= hw; i++) {
+    float v;
+    if (sigma == 0.0f) {
+      v = (i == 0) ? 1.0f : 0.0f;
+    } else {
+      long double S = sigma, I = i;
+      if ((S <= 10.0) && (fabsl(I) <= 20.0))
+        v = (float)(expl(-S * S) * std::cyl_bessel_i(fabsl(I), S * S));
+      else
+        v = (float)(expl(-(I * I) / (2.0 * S * S)) / sqrtl(2 * S * S * M_PI));
+    }
+    taps[i + hw] = v;
+    sum += v;
+  }
+  for (int i = 0; i < 2 * hw + 1; i++) taps[i] = (float)(taps[i] / sum);
+}
+
+// Response of the filter to an all-ones line of length n, float, j ascending
+// (lib/visfd/filter3d.hpp:1005-1011 via filter1d.hpp:96-101): the edge profile the
+// un-masked normalisation divides by.
+static void edge_profile(const float *taps, int hw, i64 n, i64 first, i64 count,
+                         float *d) {
+  for (i64 t = 0; t < count; t++) {
+    i64 i = first + t;
+    float acc = 0.0f;
+    for (int j = -hw; j <= hw; j++) {
+      i64 k = i - j;
+      if (k < 0 || k >= n) continue;
+      acc += taps[j + hw] * 1.0f;
+    }
+    d[t] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// device kernels
+// ---------------------------------------------------------------------------------
+constexpr int AX_R = 8;        // outputs per thread along the sweep axis
+constexpr int AX_WARPS = 8;    // warps per CTA
+constexpr int AX_TA = AX_R * AX_WARPS;  // 64 outputs along the axis per CTA
+constexpr int AX_TX = 128;     // columns per CTA (32 lanes x float4)
+constexpr int TAP_PAD_LO = 16; // zero padding below/above the taps in shared memory
+constexpr int TAP_PAD_HI = 8;
+
+__device__ __forceinline__ float4 ld4(const float *p) {
+  return __ldg(reinterpret_cast<const float4 *>(p));
+}
+
+// in/out: volumes; the sweep axis has n_axis entries with stride s_axis (floats);
+// the third ("other") dimension has stride s_other and is indexed by blockIdx.z.
+// premul (optional): multiply the input by this volume while staging (masked Z sweep).
+__global__ void __launch_bounds__(32 * AX_WARPS)
+sweep_axis_kernel(const float *__restrict__ in, float *__restrict__ out,
+                  const float *__restrict__ premul, const float *__restrict__ taps,
+                  int hw, int nx, i64 n_axis, i64 s_axis, i64 s_other, int vec_ok) {
+  extern __shared__ __align__(16) float smem[];
+  const int rows = AX_TA + 2 * hw + 8;          // staged rows (+8 zero rows for the unrolled tail)
+  float *tile = smem;                           // [rows][AX_TX]
+  float *tp = smem + (size_t)rows * AX_TX;      // padded taps, tp[k + TAP_PAD_LO]
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  const int tid = wy * 32 + lane;
+  const int x0 = blockIdx.x * AX_TX;
+  const i64 a0 = (i64)blockIdx.y * AX_TA;
+  const i64 base = (i64)blockIdx.z * s_other;
+
+  const int ntap = 2 * hw + 1;
+  for (int k = tid; k < ntap + TAP_PAD_LO + TAP_PAD_HI; k += 32 * AX_WARPS) {
+    int t = k - TAP_PAD_LO;
+    tp[k] = (t >= 0 && t < ntap) ? taps[t] : 0.0f;
+  }
+  // stage rows a0-hw .. a0-hw+rows-1 (zero outside the volume / beyond 2hw+TA)
+  const int xl = x0 + 4 * lane;
+  for (int r = wy; r < rows; r += AX_WARPS) {
+    i64 a = a0 - hw + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a >= 0 && a < n_axis && r < AX_TA + 2 * hw) {
+      const float *p = in + base + a * s_axis + xl;
+      if (vec_ok && xl + 3 < nx) {
+        v = ld4(p);
+        if (premul) {
+          float4 m = ld4(premul + base + a * s_axis + xl);
+          v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+        }
+      } else {
+        const float *pm = premul ? premul + base + a * s_axis + xl : nullptr;
+        if (xl + 0 < nx) v.x = __ldg(p + 0) * (pm ? __ldg(pm + 0) : 1.0f);
+        if (xl + 1 < nx) v.y = __ldg(p + 1) * (pm ? __ldg(pm + 1) : 1.0f);
+        if (xl + 2 < nx) v.z = __ldg(p + 2) * (pm ? __ldg(pm + 2) : 1.0f);
+        if (xl + 3 < nx) v.w = __ldg(p + 3) * (pm ? __ldg(pm + 3) : 1.0f);
+      }
+    }
+    *reinterpret_cast<float4 *>(tile + (size_t)r * AX_TX + 4 * lane) = v;
+  }
+  __syncthreads();
+
+  float4 acc[AX_R];
+#pragma unroll
+  for (int r = 0; r < AX_R; r++) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int ob = AX_R * wy;
+  const float *trow = tile + (size_t)ob * AX_TX + 4 * lane;
+  // output o=ob+r (axis position a0+o) takes input row p=ob+q with tap index
+  // 2hw + r - q;  q runs over [0, 2hw+7] in blocks of 8.
+  for (int q0 = 0; q0 < 2 * hw + AX_R; q0 += 8) {
+    float t[15];
+    const float *tb = tp + TAP_PAD_LO + (2 * hw - q0) - 7;
+#pragma unroll
+    for (int d = 0; d < 15; d++) t[d] = tb[d];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      float4 v = *reinterpret_cast<const float4 *>(trow + (size_t)(q0 + u) * AX_TX);
+#pragma unroll
+      for (int r = 0; r < AX_R; r++) {
+        float h = t[r - u + 7];
+        acc[r].x = fmaf(h, v.x, acc[r].x);
+        acc[r].y = fmaf(h, v.y, acc[r].y);
+        acc[r].z = fmaf(h, v.z, acc[r].z);
+        acc[r].w = fmaf(h, v.w, acc[r].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < AX_R; r++) {
+    i64 a = a0 + ob + r;
+    if (a >= n_axis) break;
+    float *p = out + base + a * s_axis + xl;
+    if (vec_ok && xl + 3 < nx) {
+      *reinterpret_cast<float4 *>(p) = acc[r];
+    } else {
+      if (xl + 0 < nx) p[0] = acc[r].x;
+      if (xl + 1 < nx) p[1] = acc[r].y;
+      if (xl + 2 < nx) p[2] = acc[r].z;
+      if (xl + 3 < nx) p[3] = acc[r].w;
+    }
+  }
+}
+
+constexpr int XS_ROWS = 32;  // rows per CTA (8 warps x 4 rows per thread)
+constexpr int XS_TX = 128;   // outputs along x per CTA
+constexpr int XS_RR = 4;     // rows per thread
+
+struct XEpilogue {
+  // normalisation: out = v / (dx[x]*dy[y]*dz[z]) (un-masked) or v / den3[i] where >0
+  const float *dx, *dy, *dz;   // un-masked edge profiles (NULL = no normalisation)
+  const float *den3;           // masked: 3-D denominator after its own X sweep
+  // combine: out = (minuend[i] - v) * scale when minuend != NULL (DoG / LoG)
+  const float *minuend;
+  float scale;
+};
+
+__global__ void __launch_bounds__(256)
+sweep_x_kernel(const float *__restrict__ in, float *__restrict__ out,
+               const float *__restrict__ taps, int hw, int nx, i64 nrows, int ny,
+               XEpilogue ep, int vec_ok) {
+  extern __shared__ __align__(16) float smem[];
+  const int hwpad = (hw + 3) & ~3;
+  const int pitch = XS_TX + 2 * hwpad + 4;   // +4: keeps rows 16 B aligned, staggers banks
+  float *tile = smem;                        // [XS_ROWS][pitch]
+  float *tp = smem + (size_t)XS_ROWS * pitch;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.y * XS_TX;
+  const i64 row0 = (i64)blockIdx.x * XS_ROWS;
+  const int ntap = 2 * hw + 1;
+  for (int k = tid; k < ntap + TAP_PAD_LO + TAP_PAD_HI; k += 256) {
+    int t = k - TAP_PAD_LO;
+    tp[k] = (t >= 0 && t < ntap) ? taps[t] : 0.0f;
+  }
+  // stage: each row segment covers x in [x0-hwpad, x0+XS_TX+hwpad)
+  const int segw = XS_TX + 2 * hwpad;         // multiple of 4
+  const int nvec = segw >> 2;
+  for (int r = w; r < XS_ROWS; r += 8) {
+    i64 row = row0 + r;
+    const float *prow = in + row * (i64)nx;
+    for (int c = lane; c < nvec; c += 32) {
+      int x = x0 - hwpad + 4 * c;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < nrows) {
+        if (vec_ok && x >= 0 && x + 3 < nx) {
+          v = ld4(prow + x);
+        } else {
+          if (x + 0 >= 0 && x + 0 < nx) v.x = __ldg(prow + x + 0);
+          if (x + 1 >= 0 && x + 1 < nx) v.y = __ldg(prow + x + 1);
+          if (x + 2 >= 0 && x + 2 < nx) v.z = __ldg(prow + x + 2);
+          if (x + 3 >= 0 && x + 3 < nx) v.w = __ldg(prow + x + 3);
+        }
+      }
+      *reinterpret_cast<float4 *>(tile + (size_t)r * pitch + 4 * c) = v;
+    }
+  }
+  __syncthreads();
+
+  float acc[XS_RR][4];
+#pragma unroll
+  for (int i = 0; i < XS_RR; i++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) acc[i][e] = 0.f;
+  // thread: outputs x0+4*lane+e (e=0..3) of rows w*4+i.  Input float4 step m holds
+  // tile columns 4*lane+4m+c; output e sits at column 4*lane+hwpad+e; tap index
+  // = hw + hwpad + e - c - 4m.
+  const int nsteps = (2 * hwpad + 4) >> 2;
+  const float *tb0 = tp + TAP_PAD_LO + hw + hwpad - 3;
+  const float *trow = tile + (size_t)(w * XS_RR) * pitch + 4 * lane;
+  for (int m = 0; m < nsteps; m++) {
+    float t[7];
+    const float *tb = tb0 - 4 * m;
+#pragma unroll
+    for (int d = 0; d < 7; d++) t[d] = tb[d];
+#pragma unroll
+    for (int i = 0; i < XS_RR; i++) {
+      float4 v = *reinterpret_cast<const float4 *>(trow + (size_t)i * pitch + 4 * m);
+      float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[i][e] = fmaf(t[e - c + 3], vv[c], acc[i][e]);
+    }
+  }
+  const int xo = x0 + 4 * lane;
+#pragma unroll
+  for (int i = 0; i < XS_RR; i++) {
+    i64 row = row0 + w * XS_RR + i;
+    if (row >= nrows) break;
+    float r4[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+    const i64 o = row * (i64)nx + xo;
+    if (ep.dx) {
+      const int iy = (int)(row % ny);
+      const i64 iz = row / ny;
+      const float dyz_y = __ldg(ep.dy + iy), dz = __ldg(ep.dz + iz);
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (xo + e < nx) {
+          // filter3d.hpp:1016-1019: den = (dx*dy)*dz, IEEE division
+          float den = __fmul_rn(__fmul_rn(__ldg(ep.dx + xo + e), dyz_y), dz);
+          r4[e] = __fdiv_rn(r4[e], den);
+        }
+    } else if (ep.den3) {
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (xo + e < nx) {
+          float den = __ldg(ep.den3 + o + e);
+          if (den > 0.0f) r4[e] = __fdiv_rn(r4[e], den);  // filter3d.hpp:991-992
+        }
+    }
+    if (ep.minuend) {
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (xo + e < nx) r4[e] = __fmul_rn(__fsub_rn(__ldg(ep.minuend + o + e), r4[e]), ep.scale);
+    }
+    if (vec_ok && xo + 3 < nx) {
+      *reinterpret_cast<float4 *>(out + o) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (xo + e < nx) out[o + e] = r4[e];
+    }
+  }
+}
+
+__global__ void fill_kernel(float *p, float v, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------
+// host drivers (device pointers)
+// ---------------------------------------------------------------------------------
+static void launch_axis(visfd_ctx *ctx, const float *in, float *out, const float *premul,
+                        const float *d_taps, int hw, i64 nx, i64 n_axis, i64 s_axis,
+                        i64 n_other, i64 s_other) {
+  const int rows = AX_TA + 2 * hw + 8;
+  size_t smem = ((size_t)rows * AX_TX + (2 * hw + 1 + TAP_PAD_LO + TAP_PAD_HI)) * sizeof(float);
+  VREQUIRE(smem <= 220 * 1024, "filter half-width too large for the sweep kernel (max ~180 voxels)");
+  VREQUIRE(n_other <= 65535 && div_up(n_axis, AX_TA) <= 65535, "volume too large in y/z for one launch");
+  static bool attr_set = false;
+  if (!attr_set) {
+    VCK(cudaFuncSetAttribute(sweep_axis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0) &&
+               (!premul || ((uintptr_t)premul & 15) == 0);
+  dim3 grid(div_up(nx, AX_TX), div_up(n_axis, AX_TA), (unsigned)n_other);
+  dim3 block(32, AX_WARPS);
+  sweep_axis_kernel<<<grid, block, smem, ctx->stream>>>(in, out, premul, d_taps, hw, (int)nx, n_axis,
+                                                        s_axis, s_other, vec_ok);
+  VCK(cudaGetLastError());
+  ctx->count_launch();
+}
+
+static void launch_x(visfd_ctx *ctx, const float *in, float *out, const float *d_taps, int hw,
+                     i64 nx, i64 ny, i64 nrows, const XEpilogue &ep) {
+  const int hwpad = (hw + 3) & ~3;
+  const int pitch = XS_TX + 2 * hwpad + 4;
+  size_t smem = ((size_t)XS_ROWS * pitch + (2 * hw + 1 + TAP_PAD_LO + TAP_PAD_HI)) * sizeof(float);
+  VREQUIRE(smem <= 220 * 1024, "filter half-width too large for the x sweep kernel");
+  static bool attr_set = false;
+  if (!attr_set) {
+    VCK(cudaFuncSetAttribute(sweep_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  // rows go on grid.x (2^31-1 blocks), x tiles on grid.y
+  i64 gx = (nrows + XS_ROWS - 1) / XS_ROWS;
+  VREQUIRE(gx <= 2147483647LL && div_up(nx, XS_TX) <= 65535, "volume too large for one launch");
+  dim3 grid((unsigned)gx, div_up(nx, XS_TX), 1);
+  sweep_x_kernel<<<grid, 256, smem, ctx->stream>>>(in, out, d_taps, hw, (int)nx, nrows, (int)ny, ep,
+                                                   vec_ok);
+  VCK(cudaGetLastError());
+  ctx->count_launch();
+}
+
+void fill_device(visfd_ctx *ctx, float *p, float v, i64 n) {
+  fill_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(p, v, n);
+  VCK(cudaGetLastError());
+  ctx->count_launch();
+}
+
+// ApplySeparable on device memory.  src/dst/mask: device pointers to the slab
+// (nz_local planes = global planes [z_offset, z_offset+nz_local) of nz_global).
+// tmp: device scratch of N floats (dst may not alias src).  If combine_minuend is
+// given the result written to dst is (combine_minuend - filtered) * combine_scale.
+float separable_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
+                       const float *src, float *dst, const float *mask, const float *const taps[3],
+                       const int hw[3], bool normalize, const float *combine_minuend,
+                       float combine_scale) {
+  StageTimer timer(ctx, "gauss");
+  const i64 N = nx * ny * nz_local;
+  VREQUIRE(nx > 0 && ny > 0 && nz_local > 0, "empty volume");
+  VREQUIRE(hw[0] >= 0 && hw[1] >= 0 && hw[2] >= 0, "negative filter half-width");
+  VREQUIRE(z_offset >= 0 && z_offset + nz_local <= nz_global, "slab outside the volume");
+  // upload taps (+ edge profiles) in one host buffer
+  const int nt[3] = {2 * hw[0] + 1, 2 * hw[1] + 1, 2 * hw[2] + 1};
+  const i64 n_dim[3] = {nx, ny, nz_local};
+  size_t total = nt[0] + nt[1] + nt[2] + nx + ny + nz_local;
+  std::vector<float> h(total);
+  size_t off_t[3], off_d[3], o = 0;
+  for (int d = 0; d < 3; d++) { off_t[d] = o; memcpy(&h[o], taps[d], nt[d] * sizeof(float)); o += nt[d]; }
+  for (int d = 0; d < 3; d++) { off_d[d] = o; o += n_dim[d]; }
+  bool plain_norm = normalize && !mask;
+  if (plain_norm) {
+    edge_profile(taps[0], hw[0], nx, 0, nx, &h[off_d[0]]);
+    edge_profile(taps[1], hw[1], ny, 0, ny, &h[off_d[1]]);
+    edge_profile(taps[2], hw[2], nz_global, z_offset, nz_local, &h[off_d[2]]);
+  }
+  Scratch<float> dconst(ctx, total);
+  VCK(cudaMemcpyAsync(dconst.get(), h.data(), total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  // The host vector must outlive the async copy from pageable memory: cudaMemcpyAsync
+  // from pageable memory returns after staging, so this is safe.
+  const float *tx = dconst.get() + off_t[0], *ty = dconst.get() + off_t[1], *tz = dconst.get() + off_t[2];
+
+  Scratch<float> tmp(ctx, N);
+  XEpilogue ep{};
+  ep.minuend = combine_minuend;
+  ep.scale = combine_scale;
+  if (!mask) {
+    // Z: src -> dst ; Y: dst -> tmp ; X: tmp -> dst
+    launch_axis(ctx, src, dst, nullptr, tz, hw[2], nx, nz_local, nx * ny, ny, nx);
+    launch_axis(ctx, dst, tmp.get(), nullptr, ty, hw[1], nx, ny, nx, nz_local, nx * ny);
+    if (plain_norm) {
+      ep.dx = dconst.get() + off_d[0];
+      ep.dy = dconst.get() + off_d[1];
+      ep.dz = dconst.get() + off_d[2];
+    }
+    launch_x(ctx, tmp.get(), dst, tx, hw[0], nx, ny, ny * nz_local, ep);
+  } else {
+    // masked: filter mask*src and (if normalising) the mask itself
+    // (filter3d.hpp:799-803, 868-879, 948-959, 986-992)
+    Scratch<float> den, den2;
+    launch_axis(ctx, src, dst, mask, tz, hw[2], nx, nz_local, nx * ny, ny, nx);
+    launch_axis(ctx, dst, tmp.get(), nullptr, ty, hw[1], nx, ny, nx, nz_local, nx * ny);
+    if (normalize) {
+      den.reset(ctx, N);
+      den2.reset(ctx, N);
+      XEpilogue none{};
+      launch_axis(ctx, mask, den.get(), nullptr, tz, hw[2], nx, nz_local, nx * ny, ny, nx);
+      launch_axis(ctx, den.get(), den2.get(), nullptr, ty, hw[1], nx, ny, nx, nz_local, nx * ny);
+      launch_x(ctx, den2.get(), den.get(), tx, hw[0], nx, ny, ny * nz_local, none);
+      ep.den3 = den.get();
+    }
+    launch_x(ctx, tmp.get(), dst, tx, hw[0], nx, ny, ny * nz_local, ep);
+  }
+  return taps[0][hw[0]] * taps[1][hw[1]] * taps[2][hw[2]];  // filter3d.hpp:1044-1046
+}
+
+float gauss_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
+                   const float *src, float *dst, const float *mask, const float sigma[3],
+                   const int hw[3], bool normalize, const float *combine_minuend, float combine_scale) {
+  std::vector<float> t[3];
+  const float *tp[3];
+  for (int d = 0; d < 3; d++) {
+    VREQUIRE(hw[d] >= 0 && sigma[d] >= 0.0f, "negative sigma or half-width");
+    t[d].resize(2 * hw[d] + 1);
+    gen_gauss1d(sigma[d], hw[d], t[d].data());
+    tp[d] = t[d].data();
+  }
+  return separable_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, dst, mask, tp, hw,
+                          normalize, combine_minuend, combine_scale);
+}
+
+// ApplyDog (filter3d.hpp:1340-1402): dst = G_a(src) - G_b(src), optionally * scale (ApplyLog).
+void dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
+                const float *src, float *dst, const float *mask, const float sigma_a[3],
+                const float sigma_b[3], const int hw[3], float scale, float *A, float *B) {
+  const i64 N = nx * ny * nz_local;
+  Scratch<float> ga(ctx, N);
+  float a = gauss_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, ga.get(), mask, sigma_a, hw,
+                         true, nullptr, 1.0f);
+  float b = gauss_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, dst, mask, sigma_b, hw, true,
+                         ga.get(), scale);
+  if (A) *A = a;
+  if (B) *B = b;
+}
+
+// ApplyLog parameter derivation: filter3d.hpp:1451-1464, :1493
+void log_params(const float sigma[3], float delta, float truncate_ratio, float sigma_a[3],
+                float sigma_b[3], int hw[3], float *scale) {
+  for (int d = 0; d < 3; d++) {
+    sigma_a[d] = (float)(sigma[d] * (1.0 - 0.5 * delta));
+    sigma_b[d] = (float)(sigma[d] * (1.0 + 0.5 * delta));
+    hw[d] = (int)floor(truncate_ratio * std::max(sigma_a[d], sigma_b[d]));
+  }
+  *scale = (float)(1.0 / (delta * delta));
+}
+
+}  // namespace visfd_cuda
