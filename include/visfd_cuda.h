@@ -58,6 +58,12 @@ void visfd_cuda_destroy(visfd_ctx *ctx);
 const char *visfd_cuda_last_error(void);
 /* Use an existing stream (cudaStream_t passed as void*) for all work of ctx. */
 int visfd_cuda_set_stream(visfd_ctx *ctx, void *cuda_stream);
+/* Separable-filter arithmetic.  0 (default): every tap is a separate IEEE multiply and
+ * add in the reference's accumulation order, so Gaussian / DoG / LoG outputs are
+ * bit-identical to the reference's x86-64 build.  1: one fused multiply-add per tap
+ * (half the FP32 instructions; differences ~1e-7 of the image scale).  The environment
+ * variable VISFD_CUDA_FAST_GAUSS=1 sets the initial value. */
+void visfd_cuda_set_fast_gauss(visfd_ctx *ctx, int enabled);
 /* Release cached device workspace. */
 int visfd_cuda_trim(visfd_ctx *ctx);
 /* Number of kernel launches issued by ctx since creation (bench bookkeeping). */

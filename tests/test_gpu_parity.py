@@ -4,11 +4,16 @@ same seeded inputs, and against the committed reference vectors.
 Tolerances (BASELINE.json:north_star): 1e-5 relative for Gaussian/DoG/LoG outputs,
 1e-4 for saliency and vote outputs, normals up to sign, masks / blob lists / index work
 bit-exact.  "Relative" is util.rel_err: per-voxel |a-b| / max(|b|, 1e-3 * max|b|).
+
+The separable filters are held to a stricter bar than north_star asks: in their default
+(EXACT) arithmetic mode the Gaussian / DoG / LoG / CalcHessian outputs must be
+BIT-IDENTICAL to the reference; the 1e-5 tolerance is only used for the opt-in FFMA mode.
 """
 import numpy as np
 import pytest
 
-from util import TOL_GAUSS, TOL_SALIENCY, rel_err, tensor_rel_err, direction_err, sort_blobs
+from util import (TOL_GAUSS, TOL_SALIENCY, rel_err, tensor_rel_err, direction_err, sort_blobs,
+                  vote_score_err)
 from visfd_b200 import synth
 import visfd_b200 as vb
 
@@ -44,21 +49,21 @@ def test_taps_bit_exact(golden, oracle):
 def test_gauss_golden(ctx, golden):
     vol, mask = golden["vol"], golden["mask"]
     d, A = ctx.apply_gauss(vol, 1.3, 3)
-    assert rel_err(d, golden["gauss_s1.3_hw3"]) <= TOL_GAUSS
+    assert np.array_equal(d, golden["gauss_s1.3_hw3"])
     assert np.float32(A) == golden["gauss_A"]
-    assert rel_err(ctx.apply_gauss(vol, 1.3, 3, normalize=False)[0], golden["gauss_s1.3_hw3_nonorm"]) <= TOL_GAUSS
-    assert rel_err(ctx.apply_gauss(vol, (1.0, 2.0, 0.7), (2, 5, 1))[0], golden["gauss_aniso"]) <= TOL_GAUSS
-    assert rel_err(ctx.apply_gauss(vol, 1.3, 3, mask=mask)[0], golden["gauss_masked"]) <= TOL_GAUSS
-    assert rel_err(ctx.apply_gauss(vol, 1.3, 3, mask=mask, normalize=False)[0],
-                   golden["gauss_masked_nonorm"]) <= TOL_GAUSS
-    assert rel_err(ctx.apply_gauss(vol, 4.0, 10)[0], golden["gauss_wide"]) <= TOL_GAUSS
+    assert np.array_equal(ctx.apply_gauss(vol, 1.3, 3, normalize=False)[0], golden["gauss_s1.3_hw3_nonorm"])
+    assert np.array_equal(ctx.apply_gauss(vol, (1.0, 2.0, 0.7), (2, 5, 1))[0], golden["gauss_aniso"])
+    assert np.array_equal(ctx.apply_gauss(vol, 1.3, 3, mask=mask)[0], golden["gauss_masked"])
+    assert np.array_equal(ctx.apply_gauss(vol, 1.3, 3, mask=mask, normalize=False)[0],
+                          golden["gauss_masked_nonorm"])
+    assert np.array_equal(ctx.apply_gauss(vol, 4.0, 10)[0], golden["gauss_wide"])
     d, a, b = ctx.apply_dog(vol, 1.2, 1.92, 5)
-    assert rel_err(d, golden["dog"]) <= TOL_GAUSS
+    assert np.array_equal(d, golden["dog"])
     assert np.array_equal(np.array([a, b], np.float32), golden["dog_AB"])
     d, a, b = ctx.apply_log(vol, 1.5, 0.02, 2.6482)
-    assert rel_err(d, golden["log"]) <= 20 * TOL_GAUSS  # see test_log_cancellation
-    np.testing.assert_allclose(np.array([a, b], np.float32), golden["log_AB"], rtol=1e-6)
-    assert rel_err(ctx.apply_log(vol, 1.5, 0.02, 2.6482, mask=mask)[0], golden["log_masked"]) <= 20 * TOL_GAUSS
+    assert np.array_equal(d, golden["log"])
+    assert np.array_equal(np.array([a, b], np.float32), golden["log_AB"])
+    assert np.array_equal(ctx.apply_log(vol, 1.5, 0.02, 2.6482, mask=mask)[0], golden["log_masked"])
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (3, 1, 2), (5, 7, 130), (70, 9, 33), (9, 140, 7), (64, 64, 128),
@@ -70,8 +75,22 @@ def test_gauss_shapes(ctx, oracle, shape, sigma, hw):
         shape).astype(np.float32)
     want, A0 = oracle.apply_gauss(vol, sigma, hw)
     got, A1 = ctx.apply_gauss(vol, sigma, hw)
-    assert rel_err(got, want) <= TOL_GAUSS
+    assert np.array_equal(got, want)
     assert np.float32(A0) == np.float32(A1)
+
+
+def test_gauss_fast_mode_tolerance(ctx, oracle):
+    """opt-in FFMA sweeps: |a-b| <= 1e-5 * max(|b|, 1% of the volume's max)"""
+    vol = synth.tomogram((48, 56, 72), seed=21)
+    ctx.set_fast_gauss(True)
+    try:
+        for sigma, hw in ((1.0, 2), (3.0, 7), (8.0, 21)):
+            want, _ = oracle.apply_gauss(vol, sigma, hw)
+            got, _ = ctx.apply_gauss(vol, sigma, hw)
+            assert rel_err(got, want, floor_frac=1e-2) <= TOL_GAUSS
+            assert np.abs(got - want).max() <= 4e-7 * np.abs(want).max()
+    finally:
+        ctx.set_fast_gauss(False)
 
 
 def test_gauss_masked_and_device_path(ctx, oracle):
@@ -83,7 +102,7 @@ def test_gauss_masked_and_device_path(ctx, oracle):
     for normalize in (True, False):
         want, _ = oracle.apply_gauss(vol, 2.0, 5, mask=mask, normalize=normalize)
         got, _ = ctx.apply_gauss(vol, 2.0, 5, mask=mask, normalize=normalize)
-        assert rel_err(got, want) <= TOL_GAUSS
+        assert np.array_equal(got, want)
         # device-resident path: same kernels, no staging
         got_d, _ = ctx.apply_gauss(torch.from_numpy(vol).cuda(), 2.0, 5, mask=torch.from_numpy(mask).cuda(),
                                    normalize=normalize)
@@ -92,30 +111,21 @@ def test_gauss_masked_and_device_path(ctx, oracle):
     tx, ty, tz = (vb.gen_gauss1d(s, h) for s, h in ((1.0, 3), (2.5, 6), (0.7, 2)))
     want, _ = oracle.apply_gauss(vol, (1.0, 2.5, 0.7), (3, 6, 2))
     got, _ = ctx.apply_separable(vol, (tx, ty, tz))
-    assert rel_err(got, want) <= TOL_GAUSS
+    assert np.array_equal(got, want)
 
 
 def test_dog_log(ctx, oracle):
     vol = synth.tomogram((48, 40, 56), seed=4)
     want, a0, b0 = oracle.apply_dog(vol, 2.0, 3.2, 8)
     got, a1, b1 = ctx.apply_dog(vol, 2.0, 3.2, 8)
-    assert rel_err(got, want) <= TOL_GAUSS
+    assert np.array_equal(got, want)
     assert (np.float32(a0), np.float32(b0)) == (np.float32(a1), np.float32(b1))
-
-
-def test_log_cancellation(ctx, oracle):
-    """ApplyLog subtracts two Gaussians that differ by 2 % in sigma and multiplies by
-    1/delta^2 = 2500: a 1e-7 rounding difference in either Gaussian is a ~1e-4 relative
-    difference of the result.  The Gaussians themselves meet 1e-5; the LoG is judged at
-    the tolerance that follows from it and against the reference's own sensitivity."""
+    # ApplyLog: a difference of two Gaussians 2 % apart in sigma times 1/delta^2 = 2500 --
+    # only bit-exact Gaussians make this reproducible
     vol = synth.tomogram((40, 44, 48), seed=6, blobs=4)
     want, _, _ = oracle.apply_log(vol, 2.0, 0.02, 2.6482)
     got, _, _ = ctx.apply_log(vol, 2.0, 0.02, 2.6482)
-    assert rel_err(got, want) <= 2e-4
-    # scale check: the reference's own response to a 1-ulp perturbation of its input
-    pert = np.nextafter(vol, np.float32(np.inf))
-    want_p, _, _ = oracle.apply_log(pert, 2.0, 0.02, 2.6482)
-    assert rel_err(got, want) <= 50 * max(rel_err(want_p, want), 1e-6)
+    assert np.array_equal(got, want)
 
 
 def test_gauss_linearity_and_constant(ctx):
@@ -127,7 +137,7 @@ def test_gauss_linearity_and_constant(ctx):
     ga, _ = ctx.apply_gauss(a, 3.0, 7)
     gb, _ = ctx.apply_gauss(b, 3.0, 7)
     gab, _ = ctx.apply_gauss(a + 2 * b, 3.0, 7)
-    assert rel_err(gab, ga + 2 * gb) <= 2e-5
+    assert rel_err(gab, ga + 2 * gb, floor_frac=1e-2) <= 2e-5
     gc, _ = ctx.apply_gauss(np.full(shape, 3.25, np.float32), 3.0, 7)
     assert np.abs(gc - 3.25).max() <= 3.25 * 1e-6
 
@@ -150,11 +160,11 @@ def test_gauss_slab_equals_whole(ctx):
 def test_calc_hessian(ctx, oracle, golden):
     vol, mask = golden["vol"], golden["mask"]
     g, h = ctx.calc_hessian(vol, 1.1, 2.6482)
-    assert rel_err(g, golden["hess_grad"]) <= 1e-4
-    assert rel_err(h, golden["hess_hess"]) <= 1e-4
+    assert np.array_equal(g, golden["hess_grad"])
+    assert np.array_equal(h, golden["hess_hess"])
     g, h = ctx.calc_hessian(vol, 1.1, 2.6482, mask=mask)
-    assert rel_err(g, golden["hess_grad_masked"]) <= 1e-4
-    assert rel_err(h, golden["hess_hess_masked"]) <= 1e-4
+    assert np.array_equal(g, golden["hess_grad_masked"])
+    assert np.array_equal(h, golden["hess_hess_masked"])
     assert np.all(h[mask == 0] == 0)
 
 
@@ -271,7 +281,10 @@ def test_tv_single_voter_support(ctx, oracle):
         want = oracle.tv_dense_stick(sal, dire, sigma_tv, 4, SQ2)
         got = ctx.tv_dense_stick(sal, dire, sigma_tv, 4, SQ2)
         tw, tg = np.abs(want).sum(-1), np.abs(got).sum(-1)
-        assert np.array_equal(tw != 0, tg != 0)
+        # same support: every voxel the reference votes on (above rounding dust: votes along
+        # the stick axis are exactly 0 there, ~1e-14 here) and nothing outside its table
+        assert np.all(tg[tw > 1e-6 * tw.max()] > 0)
+        assert np.all(tg[tw == 0] <= 1e-9 * tw.max())
         assert tensor_rel_err(got, want) <= TOL_SALIENCY
 
 
@@ -309,16 +322,22 @@ def test_membrane_pipeline_vs_oracle(ctx, oracle):
     -tv-best 0.05) on a volume the oracle finishes in seconds"""
     vol = synth.tomogram((56, 60, 64), seed=14, n_shells=2)
     sigma, ratio, tv_sigma = 2.99991, 2.6482, 14.1986
-    want = oracle.membrane(vol, sigma, ratio, 1, 0.05, True, tv_sigma, 4, SQ2, want_tensor=False)
-    got = ctx.membrane(vol, sigma, ratio, 1, 0.05, True, tv_sigma, 4, SQ2, want_saliency=True)
-    assert rel_err(got["threshold"], want["threshold"]) <= TOL_SALIENCY
-    # survivors of the cut: identical except voxels within tolerance of the threshold
-    thr = want["threshold"]
-    differ = (got["hess_saliency"] != 0) != (want["hess_saliency"] != 0)
-    pre = oracle.membrane(vol, sigma, ratio, 1, 0.0, False, 0.0, 4, SQ2)["out"]
-    assert np.all(np.abs(pre[differ] - thr) <= TOL_SALIENCY * thr)
-    if not differ.any():
-        assert rel_err(got["out"], want["out"]) <= TOL_SALIENCY
+    want = oracle.membrane(vol, sigma, ratio, 1, 0.05, True, tv_sigma, 4, SQ2, want_tensor=True)
+    got = ctx.membrane(vol, sigma, ratio, 1, 0.05, True, tv_sigma, 4, SQ2, want_saliency=True, want_tensor=True)
+    # Gaussian + finite differences are bit-exact and the eigenvalues agree to double
+    # rounding, so the cut threshold and the set of surviving voxels are IDENTICAL
+    assert np.float32(got["threshold"]) == np.float32(want["threshold"])
+    assert np.array_equal(got["hess_saliency"] != 0, want["hess_saliency"] != 0)
+    assert rel_err(got["hess_saliency"], want["hess_saliency"], floor_frac=1e-6) <= TOL_SALIENCY
+    assert tensor_rel_err(got["tensor"], want["tensor"]) <= TOL_SALIENCY
+    assert vote_score_err(got["out"], want["out"], want["tensor"]) <= TOL_SALIENCY
+    # thresholded mask of the result (-thresh at the 99th percentile): bit-exact except
+    # voxels within tolerance of the threshold
+    T = float(np.quantile(want["out"], 0.99))
+    ma = ctx.threshold(got["out"], vb.THRESH_SINGLE, [T])
+    mb = oracle.threshold1(want["out"], T)
+    differ = ma != mb
+    assert np.all(np.abs(want["out"][differ] - T) <= TOL_SALIENCY * T)
 
 
 def test_membrane_device_path_identical(ctx):
@@ -369,8 +388,7 @@ def test_blob_dog_lists_exact(ctx, oracle, golden):
             want = sort_blobs(golden[name])
             got = sort_blobs(got)
             assert got.shape == want.shape
-            assert np.array_equal(got[:, :4], want[:, :4])              # positions and scales: exact
-            np.testing.assert_allclose(got[:, 4], want[:, 4], rtol=2e-4)  # LoG scores (see test_log_cancellation)
+            assert np.array_equal(got, want)      # positions, scales AND scores: bit-exact
 
 
 def test_blob_dog_masked_vs_oracle(ctx, oracle):
@@ -384,4 +402,4 @@ def test_blob_dog_masked_vs_oracle(ctx, oracle):
                        use_threshold_ratios=False)
     for g, w in zip(got, want):
         g, w = sort_blobs(g), sort_blobs(w)
-        assert g.shape == w.shape and np.array_equal(g[:, :4], w[:, :4])
+        assert g.shape == w.shape and np.array_equal(g, w)

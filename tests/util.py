@@ -53,3 +53,18 @@ def sort_blobs(t):
         return t.reshape(0, 5)
     idx = np.lexsort((t[:, 0], t[:, 1], t[:, 2], t[:, 3]))
     return t[idx]
+
+
+def vote_score_err(a, b, tensor_ref):
+    """Error of the post-vote score lambda1 - lambda2 (ScoreTensorPlanar).  The score is a
+    DIFFERENCE of eigenvalues of a float32-accumulated tensor: where the tensor is nearly
+    isotropic (inside a closed membrane) the score is orders of magnitude smaller than the
+    tensor itself and carries the tensor's absolute rounding noise, the reference's own
+    included.  It is therefore judged against max(|b|, 10 % of trace(T_ref)), floored at
+    1e-3 of the volume's maximum."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    t = np.asarray(tensor_ref, np.float64)
+    tr = t[..., 0] + t[..., 1] + t[..., 2]
+    den = np.maximum(np.maximum(np.abs(b), 0.1 * tr), 1e-3 * np.abs(b).max())
+    return float((np.abs(a - b) / den).max())

@@ -54,6 +54,7 @@ def load_library():
     lib.visfd_cuda_stage_ms.restype = _d
     lib.visfd_cuda_key_to_float.restype = _f
     lib.visfd_cuda_set_timing.restype = None
+    lib.visfd_cuda_set_fast_gauss.restype = None
     lib.visfd_cuda_destroy.restype = None
     lib.visfd_cuda_gen_gauss1d.restype = None
     _lib = lib
@@ -167,6 +168,10 @@ class Context:
 
     def set_timing(self, enabled):
         self.lib.visfd_cuda_set_timing(self.h, _i(int(enabled)))
+
+    def set_fast_gauss(self, enabled):
+        """FFMA sweeps (fast) instead of the default bit-exact mul+add sweeps."""
+        self.lib.visfd_cuda_set_fast_gauss(self.h, _i(int(enabled)))
 
     def trim(self):
         self._ck(self.lib.visfd_cuda_trim(self.h))

@@ -46,6 +46,7 @@ struct visfd_ctx {
   bool own_stream = false;
   int64_t launches = 0;
   int64_t last_voters = 0;
+  bool fast_gauss = false;                  // FFMA sweeps instead of the bit-exact mul+add
   bool timing = true;                       // record per-stage CUDA events
   std::map<std::string, double> stage_ms;   // resolved at the end of each API call
   struct PendingEvent { const char *name; cudaEvent_t a, b; };

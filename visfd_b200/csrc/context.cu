@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
 
 namespace visfd_cuda {
 
@@ -138,6 +139,8 @@ int visfd_cuda_init(int device, visfd_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     VCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
+    const char *fg = getenv("VISFD_CUDA_FAST_GAUSS");
+    c->fast_gauss = fg && fg[0] == '1';
     *out = c;
     return 0;
   } catch (const std::exception &ex) {
@@ -176,6 +179,10 @@ int visfd_cuda_trim(visfd_ctx *ctx) {
 }
 
 int64_t visfd_cuda_launch_count(visfd_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+void visfd_cuda_set_fast_gauss(visfd_ctx *ctx, int enabled) {
+  if (ctx) ctx->fast_gauss = enabled != 0;
+}
 
 void visfd_cuda_set_timing(visfd_ctx *ctx, int enabled) {
   if (ctx) ctx->timing = enabled != 0;

@@ -17,6 +17,20 @@
 //      reading shared memory as conflict-free float4.
 // Out-of-volume taps are zero (the reference skips them, filter1d.hpp:98-99); the
 // renormalisation divides by the product of the three 1-D edge profiles.
+//
+// Arithmetic modes (template parameter MODE of both kernels):
+//  EXACT (default)  every tap is a separate IEEE multiply and add, accumulated in the
+//      reference's order (filter index j ascending = input index descending,
+//      filter1d.hpp:96-101), so the output is BIT-IDENTICAL to the reference's
+//      x86-64 (non-FMA) build.  Zero-padded taps / rows add +-0 and change nothing.
+//      This is what makes DoG/LoG (a 2500x amplified difference of two Gaussians), the
+//      blob extremum tests and the ridge saliency (4th power of second differences)
+//      reproducible rather than "close".
+//  EXACT_MASKED  Z sweep with a mask: (h*m)*f per tap as in filter1d.hpp:273-286, from
+//      two shared-memory tiles.
+//  FAST  one FFMA per tap (and mask pre-multiplied while staging): half the FP32
+//      instructions, ~1e-7 absolute / 1e-5 relative differences from the reference.
+//      Selected per context (visfd_cuda_set_fast_gauss / VISFD_CUDA_FAST_GAUSS=1).
 #include "common.cuh"
 #include "kernels.cuh"
 #include <cmath>
@@ -80,17 +94,28 @@ __device__ __forceinline__ float4 ld4(const float *p) {
   return __ldg(reinterpret_cast<const float4 *>(p));
 }
 
+enum { MODE_FAST = 0, MODE_EXACT = 1, MODE_EXACT_MASKED = 2 };
+
+template <int MODE>
+__device__ __forceinline__ float tap_acc(float acc, float h, float v) {
+  if (MODE == MODE_FAST) return fmaf(h, v, acc);
+  return __fadd_rn(acc, __fmul_rn(h, v));
+}
+
 // in/out: volumes; the sweep axis has n_axis entries with stride s_axis (floats);
 // the third ("other") dimension has stride s_other and is indexed by blockIdx.z.
-// premul (optional): multiply the input by this volume while staging (masked Z sweep).
+// mask (optional): FAST: multiplied into the input while staging; EXACT_MASKED: staged
+// in a second tile and multiplied into the TAP first, as the reference does.
+template <int MODE>
 __global__ void __launch_bounds__(32 * AX_WARPS)
 sweep_axis_kernel(const float *__restrict__ in, float *__restrict__ out,
-                  const float *__restrict__ premul, const float *__restrict__ taps,
+                  const float *__restrict__ mask, const float *__restrict__ taps,
                   int hw, int nx, i64 n_axis, i64 s_axis, i64 s_other, int vec_ok) {
   extern __shared__ __align__(16) float smem[];
   const int rows = AX_TA + 2 * hw + 8;          // staged rows (+8 zero rows for the unrolled tail)
   float *tile = smem;                           // [rows][AX_TX]
-  float *tp = smem + (size_t)rows * AX_TX;      // padded taps, tp[k + TAP_PAD_LO]
+  float *mtile = smem + (size_t)rows * AX_TX;   // [rows][AX_TX], EXACT_MASKED only
+  float *tp = smem + (size_t)rows * AX_TX * (MODE == MODE_EXACT_MASKED ? 2 : 1);  // padded taps
   const int lane = threadIdx.x, wy = threadIdx.y;
   const int tid = wy * 32 + lane;
   const int x0 = blockIdx.x * AX_TX;
@@ -106,24 +131,23 @@ sweep_axis_kernel(const float *__restrict__ in, float *__restrict__ out,
   const int xl = x0 + 4 * lane;
   for (int r = wy; r < rows; r += AX_WARPS) {
     i64 a = a0 - hw + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), m = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a >= 0 && a < n_axis && r < AX_TA + 2 * hw) {
       const float *p = in + base + a * s_axis + xl;
+      const float *pm = mask ? mask + base + a * s_axis + xl : nullptr;
       if (vec_ok && xl + 3 < nx) {
         v = ld4(p);
-        if (premul) {
-          float4 m = ld4(premul + base + a * s_axis + xl);
-          v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
-        }
+        if (pm) m = ld4(pm);
       } else {
-        const float *pm = premul ? premul + base + a * s_axis + xl : nullptr;
-        if (xl + 0 < nx) v.x = __ldg(p + 0) * (pm ? __ldg(pm + 0) : 1.0f);
-        if (xl + 1 < nx) v.y = __ldg(p + 1) * (pm ? __ldg(pm + 1) : 1.0f);
-        if (xl + 2 < nx) v.z = __ldg(p + 2) * (pm ? __ldg(pm + 2) : 1.0f);
-        if (xl + 3 < nx) v.w = __ldg(p + 3) * (pm ? __ldg(pm + 3) : 1.0f);
+        if (xl + 0 < nx) { v.x = __ldg(p + 0); if (pm) m.x = __ldg(pm + 0); }
+        if (xl + 1 < nx) { v.y = __ldg(p + 1); if (pm) m.y = __ldg(pm + 1); }
+        if (xl + 2 < nx) { v.z = __ldg(p + 2); if (pm) m.z = __ldg(pm + 2); }
+        if (xl + 3 < nx) { v.w = __ldg(p + 3); if (pm) m.w = __ldg(pm + 3); }
       }
+      if (MODE == MODE_FAST && pm) { v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w; }
     }
     *reinterpret_cast<float4 *>(tile + (size_t)r * AX_TX + 4 * lane) = v;
+    if (MODE == MODE_EXACT_MASKED) *reinterpret_cast<float4 *>(mtile + (size_t)r * AX_TX + 4 * lane) = m;
   }
   __syncthreads();
 
@@ -132,23 +156,36 @@ sweep_axis_kernel(const float *__restrict__ in, float *__restrict__ out,
   for (int r = 0; r < AX_R; r++) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int ob = AX_R * wy;
   const float *trow = tile + (size_t)ob * AX_TX + 4 * lane;
+  const float *mrow = mtile + (size_t)ob * AX_TX + 4 * lane;
   // output o=ob+r (axis position a0+o) takes input row p=ob+q with tap index
-  // 2hw + r - q;  q runs over [0, 2hw+7] in blocks of 8.
-  for (int q0 = 0; q0 < 2 * hw + AX_R; q0 += 8) {
+  // 2hw + r - q;  q runs over [0, 2hw+7] in blocks of 8, from the HIGHEST input index
+  // down: that is the reference's accumulation order (tap index ascending).
+  const int nblk = (2 * hw + AX_R + 7) / 8;
+  for (int q0 = 8 * (nblk - 1); q0 >= 0; q0 -= 8) {
     float t[15];
     const float *tb = tp + TAP_PAD_LO + (2 * hw - q0) - 7;
 #pragma unroll
     for (int d = 0; d < 15; d++) t[d] = tb[d];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
+    for (int u = 7; u >= 0; u--) {
       float4 v = *reinterpret_cast<const float4 *>(trow + (size_t)(q0 + u) * AX_TX);
+      float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (MODE == MODE_EXACT_MASKED) m = *reinterpret_cast<const float4 *>(mrow + (size_t)(q0 + u) * AX_TX);
 #pragma unroll
       for (int r = 0; r < AX_R; r++) {
         float h = t[r - u + 7];
-        acc[r].x = fmaf(h, v.x, acc[r].x);
-        acc[r].y = fmaf(h, v.y, acc[r].y);
-        acc[r].z = fmaf(h, v.z, acc[r].z);
-        acc[r].w = fmaf(h, v.w, acc[r].w);
+        if (MODE == MODE_EXACT_MASKED) {
+          // filter1d.hpp:273-286: filter_val = h*mask; delta = filter_val*f; g += delta
+          acc[r].x = __fadd_rn(acc[r].x, __fmul_rn(__fmul_rn(h, m.x), v.x));
+          acc[r].y = __fadd_rn(acc[r].y, __fmul_rn(__fmul_rn(h, m.y), v.y));
+          acc[r].z = __fadd_rn(acc[r].z, __fmul_rn(__fmul_rn(h, m.z), v.z));
+          acc[r].w = __fadd_rn(acc[r].w, __fmul_rn(__fmul_rn(h, m.w), v.w));
+        } else {
+          acc[r].x = tap_acc<MODE>(acc[r].x, h, v.x);
+          acc[r].y = tap_acc<MODE>(acc[r].y, h, v.y);
+          acc[r].z = tap_acc<MODE>(acc[r].z, h, v.z);
+          acc[r].w = tap_acc<MODE>(acc[r].w, h, v.w);
+        }
       }
     }
   }
@@ -181,6 +218,7 @@ struct XEpilogue {
   float scale;
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(256)
 sweep_x_kernel(const float *__restrict__ in, float *__restrict__ out,
                const float *__restrict__ taps, int hw, int nx, i64 nrows, int ny,
@@ -234,7 +272,8 @@ sweep_x_kernel(const float *__restrict__ in, float *__restrict__ out,
   const int nsteps = (2 * hwpad + 4) >> 2;
   const float *tb0 = tp + TAP_PAD_LO + hw + hwpad - 3;
   const float *trow = tile + (size_t)(w * XS_RR) * pitch + 4 * lane;
-  for (int m = 0; m < nsteps; m++) {
+  // highest input column first = the reference's accumulation order (tap index ascending)
+  for (int m = nsteps - 1; m >= 0; m--) {
     float t[7];
     const float *tb = tb0 - 4 * m;
 #pragma unroll
@@ -246,7 +285,7 @@ sweep_x_kernel(const float *__restrict__ in, float *__restrict__ out,
 #pragma unroll
       for (int e = 0; e < 4; e++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc[i][e] = fmaf(t[e - c + 3], vv[c], acc[i][e]);
+        for (int c = 3; c >= 0; c--) acc[i][e] = tap_acc<MODE>(acc[i][e], t[e - c + 3], vv[c]);
     }
   }
   const int xo = x0 + 4 * lane;
@@ -299,26 +338,39 @@ __global__ void fill_kernel(float *p, float v, i64 n) {
 // ---------------------------------------------------------------------------------
 // host drivers (device pointers)
 // ---------------------------------------------------------------------------------
-static void launch_axis(visfd_ctx *ctx, const float *in, float *out, const float *premul,
-                        const float *d_taps, int hw, i64 nx, i64 n_axis, i64 s_axis,
-                        i64 n_other, i64 s_other) {
+template <int MODE>
+static void launch_axis_mode(visfd_ctx *ctx, const float *in, float *out, const float *mask,
+                             const float *d_taps, int hw, i64 nx, i64 n_axis, i64 s_axis,
+                             i64 n_other, i64 s_other) {
   const int rows = AX_TA + 2 * hw + 8;
-  size_t smem = ((size_t)rows * AX_TX + (2 * hw + 1 + TAP_PAD_LO + TAP_PAD_HI)) * sizeof(float);
-  VREQUIRE(smem <= 220 * 1024, "filter half-width too large for the sweep kernel (max ~180 voxels)");
+  size_t smem = ((size_t)rows * AX_TX * (MODE == MODE_EXACT_MASKED ? 2 : 1) +
+                 (2 * hw + 1 + TAP_PAD_LO + TAP_PAD_HI)) * sizeof(float);
+  VREQUIRE(smem <= 220 * 1024, "filter half-width too large for the sweep kernel");
   VREQUIRE(n_other <= 65535 && div_up(n_axis, AX_TA) <= 65535, "volume too large in y/z for one launch");
   static bool attr_set = false;
   if (!attr_set) {
-    VCK(cudaFuncSetAttribute(sweep_axis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    VCK(cudaFuncSetAttribute(sweep_axis_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0) &&
-               (!premul || ((uintptr_t)premul & 15) == 0);
+               (!mask || ((uintptr_t)mask & 15) == 0);
   dim3 grid(div_up(nx, AX_TX), div_up(n_axis, AX_TA), (unsigned)n_other);
   dim3 block(32, AX_WARPS);
-  sweep_axis_kernel<<<grid, block, smem, ctx->stream>>>(in, out, premul, d_taps, hw, (int)nx, n_axis,
-                                                        s_axis, s_other, vec_ok);
+  sweep_axis_kernel<MODE><<<grid, block, smem, ctx->stream>>>(in, out, mask, d_taps, hw, (int)nx, n_axis,
+                                                              s_axis, s_other, vec_ok);
   VCK(cudaGetLastError());
   ctx->count_launch();
+}
+
+static void launch_axis(visfd_ctx *ctx, const float *in, float *out, const float *mask,
+                        const float *d_taps, int hw, i64 nx, i64 n_axis, i64 s_axis,
+                        i64 n_other, i64 s_other) {
+  if (ctx->fast_gauss)
+    launch_axis_mode<MODE_FAST>(ctx, in, out, mask, d_taps, hw, nx, n_axis, s_axis, n_other, s_other);
+  else if (mask)
+    launch_axis_mode<MODE_EXACT_MASKED>(ctx, in, out, mask, d_taps, hw, nx, n_axis, s_axis, n_other, s_other);
+  else
+    launch_axis_mode<MODE_EXACT>(ctx, in, out, mask, d_taps, hw, nx, n_axis, s_axis, n_other, s_other);
 }
 
 static void launch_x(visfd_ctx *ctx, const float *in, float *out, const float *d_taps, int hw,
@@ -329,7 +381,8 @@ static void launch_x(visfd_ctx *ctx, const float *in, float *out, const float *d
   VREQUIRE(smem <= 220 * 1024, "filter half-width too large for the x sweep kernel");
   static bool attr_set = false;
   if (!attr_set) {
-    VCK(cudaFuncSetAttribute(sweep_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    VCK(cudaFuncSetAttribute(sweep_x_kernel<MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    VCK(cudaFuncSetAttribute(sweep_x_kernel<MODE_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
@@ -337,8 +390,10 @@ static void launch_x(visfd_ctx *ctx, const float *in, float *out, const float *d
   i64 gx = (nrows + XS_ROWS - 1) / XS_ROWS;
   VREQUIRE(gx <= 2147483647LL && div_up(nx, XS_TX) <= 65535, "volume too large for one launch");
   dim3 grid((unsigned)gx, div_up(nx, XS_TX), 1);
-  sweep_x_kernel<<<grid, 256, smem, ctx->stream>>>(in, out, d_taps, hw, (int)nx, nrows, (int)ny, ep,
-                                                   vec_ok);
+  if (ctx->fast_gauss)
+    sweep_x_kernel<MODE_FAST><<<grid, 256, smem, ctx->stream>>>(in, out, d_taps, hw, (int)nx, nrows, (int)ny, ep, vec_ok);
+  else
+    sweep_x_kernel<MODE_EXACT><<<grid, 256, smem, ctx->stream>>>(in, out, d_taps, hw, (int)nx, nrows, (int)ny, ep, vec_ok);
   VCK(cudaGetLastError());
   ctx->count_launch();
 }
