@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- the membrane + tensor-voting pipeline of filter_mrc on synthetic tomograms.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path
+
+A "step" is one pass of HandleTV's pipeline (bin/filter_mrc/handlers.cpp:1618-1892:
+Gaussian -> Hessian/eigen ridge saliency -> `-tv-best` cut -> TV3D stick voting ->
+post-vote planar score) over the workload volume.  Workload = BASELINE.json config 4
+(C4): 2048 x 2048 x 1024 float32, membrane sigma 3 voxels (thickness 5.196), `-tv 4.733`
+(sigma_tv 14.2, vote radius 20), exponent 4, `-tv-best 0.05`; it fits one B200.  With
+N > 1 the SAME volume is split into N Z-slabs (strong scaling); ranks exchange raw-source
+halos by NCCL send/recv and all-reduce the cut histograms.
+
+`value`  : voxels of the whole volume / device time of one step, inputs resident in HBM.
+`e2e`    : the same through the public call with HOST (pinned) buffers: H2D of the
+           source and D2H of the result inside the timed region.
+`roofline`: the dominant kernel (tv_gather_kernel): 35 FLOP per (receiver, voter) pair
+            x the exact pair count / the kernel's CUDA-event time, against
+           the FP32 FMA peak measured in this run (MEASURED_PEAKS.json has no FP32 figure).
+`cpu_baseline`: the unmodified reference (oracle/_ref) on a bounded crop, all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gvoxel/s of filter_mrc membrane+TV pipeline"
+SQ2 = float(np.float32(np.sqrt(2.0)))
+# C4 parameters exactly as filter_mrc derives them (settings.cpp:2774, :3535-3540; handlers.cpp:1574)
+SIGMA = float(np.float32(np.float32(5.196) / np.sqrt(3.0)))
+TV_SIGMA = float(np.float32(np.float32(4.733) * np.float32(SIGMA)))
+RATIO = float(np.float32(np.sqrt(np.float32(-2) * np.log(np.float32(0.03)))))
+TV_BEST = 0.05
+WORKLOADS = {"C4": (1024, 2048, 2048), "C2": (512, 512, 512), "dev": (256, 256, 256)}
+CPU_SAMPLE = (128, 128, 128)
+# dram__bytes_read.sum + dram__bytes_write.sum of one tv_gather_kernel launch, from the
+# `ncu --set full` capture of the named workload (profiles/r01_tv_gather_ncu_full.csv)
+NCU_TRAFFIC_BYTES = {"dev": 27.629568e6 + 15.575552e6}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("VISFD_BENCH_WORKLOAD", "C4"))
+    ap.add_argument("--shape", default=None, help="nz,ny,nx override (development)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(shape, seed=0):
+    """One pass of the UNMODIFIED reference (oracle/_ref, OpenMP on all host cores) over a
+    crop of the workload; returns (seconds, cores, kind)."""
+    from oracle.pyoracle import Oracle, have
+    from visfd_b200 import synth
+    kind = "reference" if have("reference") else "port"
+    o = Oracle(kind)
+    vol = synth.tomogram(shape, seed=seed)
+    t = time.perf_counter()
+    o.membrane(vol, SIGMA, RATIO, 1, TV_BEST, True, TV_SIGMA, 4, SQ2, want_tensor=False)
+    return time.perf_counter() - t, os.cpu_count(), kind
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path, timed on the
+    host cores on a bounded sample of the workload (a 96^3 crop with the C4 parameters)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    shape = WORKLOADS.get(args.workload, WORKLOADS["C4"])
+    for _ in range(args.warmup):
+        cpu_reference_run(CPU_SAMPLE)
+    ts = []
+    cores, kind = os.cpu_count(), "reference"
+    for _ in range(args.steps):
+        dt, cores, kind = cpu_reference_run(CPU_SAMPLE)
+        ts.append(dt)
+    dt = float(np.mean(ts))
+    val = np.prod(CPU_SAMPLE) / dt / 1e9
+    sample = ("%dx%dx%d crop of the synthetic workload, same parameters (sigma 3, vote radius 20, "
+              "tv-best 0.05), one full pipeline pass per step" % CPU_SAMPLE)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gvoxel/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, shape),
+            "cpu_baseline": {"value": val, "unit": "Gvoxel/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(name, shape):
+    return {"workload": f"{name}: membrane detection (Hessian ridge saliency + TV3D stick voting) on "
+                        f"{shape[2]}x{shape[1]}x{shape[0]} float32",
+            "shape_zyx": list(shape), "sigma_vox": SIGMA, "gauss_halfwidth": 7, "tv_sigma_vox": TV_SIGMA,
+            "tv_halfwidth": 20, "tv_exponent": 4, "tv_best": TV_BEST, "partition": "z-slabs",
+            "l2": "inputs (>= 0.5 GB per volume) exceed the 126 MB L2; no flush needed"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import visfd_b200
+    from visfd_b200 import synth, MembraneParams
+    from visfd_b200.slab import SlabMembrane
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    name = args.workload
+    shape = WORKLOADS[name]
+    if args.shape:
+        shape = tuple(int(v) for v in args.shape.split(","))
+        name = "custom"
+    nz, ny, nx = shape
+    # C4 needs ~100 GB of HBM on one GPU; fall back (and say so) on a smaller device
+    free_b, total_b = torch.cuda.mem_get_info()
+    need = 6.5 * 4 * nz * ny * nx / world
+    if need > free_b and name == "C4":
+        name, shape = "C2", WORKLOADS["C2"]
+        nz, ny, nx = shape
+
+    ctx = visfd_b200.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    params = MembraneParams(SIGMA, RATIO, visfd_b200.DECREASING_EIVALS, TV_BEST, 1, TV_SIGMA, 4, SQ2)
+    pipe = SlabMembrane(ctx, shape, params, rank=rank, world=world, dist=dist if world > 1 else None, device=dev)
+    z0, z1 = pipe.plan.own
+    own = synth.tomogram_torch(shape, dev, seed=0, z0=z0, z1=z1)
+    out = torch.empty_like(own)
+    n_vox = float(nz) * ny * nx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        if world == 1:
+            ctx.reset_stage_ms()
+            ctx.membrane(own, SIGMA, RATIO, visfd_b200.DECREASING_EIVALS, TV_BEST, True, TV_SIGMA, 4, SQ2, out=out)
+        else:
+            pipe.run(own, out=out)
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    # ---- device-resident throughput -----------------------------------------------------
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ms_step = timed(device_step, args.steps)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    stage = {k: ctx.stage_ms(k) for k in ("gauss", "ridge", "select", "compact", "tv")}   # last step, this rank
+    n_voters = ctx.last_voter_count()
+    lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(lt)
+    launches = int(lt.item())
+
+    # ---- roofline of the dominant kernel (rank 0's launch) ----------------------------------
+    if world == 1:
+        r = ctx.membrane(own, SIGMA, RATIO, visfd_b200.DECREASING_EIVALS, TV_BEST, True, 0.0, 4, SQ2)
+        sal_after_cut, recv = r["out"], None
+        del r
+        pairs = ctx.tv_count_pairs(sal_after_cut, -np.inf, 20, recv=recv)
+        del sal_after_cut
+    else:
+        v0, v1 = pipe.plan.vote_local
+        o0, o1 = pipe.plan.own_local
+        pairs = ctx.tv_count_pairs(pipe.saliency[v0:v1], pipe.threshold, 20, recv=(o0 - v0, o1 - v0))
+    fp32_peak = ctx.fp32_peak(300.0)
+    tv_ms = stage["tv"]
+    achieved = 35.0 * pairs / (tv_ms * 1e-3) / 1e12
+    roofline = {"kernel": "tv_gather_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
+                "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                "traffic": NCU_TRAFFIC_BYTES.get(name) if world == 1 else None,
+                "peak_source": "measured in this run: register-resident FFMA chains (visfd_cuda_fp32_peak); "
+                               "MEASURED_PEAKS.json holds HBM and bf16 tensor peaks only",
+                "algorithmic_flop": 35.0 * pairs, "pairs": int(pairs), "voters": int(n_voters),
+                "kernel_ms": tv_ms, "share_of_step": tv_ms / ms_step}
+
+    # ---- Gaussian stage against the HBM roofline (second half of BASELINE's metric) ---------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    own_planes = z1 - z0
+    n_slab_vox = float(pipe.plan.slab[1] - pipe.plan.slab[0]) * ny * nx
+    gauss = {"bound": "hbm", "achieved": 24.0 * n_slab_vox / (stage["gauss"] * 1e-3) / 1e9, "peak": hbm_peak,
+             "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
+             "algorithmic_bytes_per_voxel": 24, "kernel_ms": stage["gauss"]}
+    gauss["frac"] = gauss["achieved"] / hbm_peak
+    ridge = {"bound": "hbm", "achieved": 8.0 * n_slab_vox / (stage["ridge"] * 1e-3) / 1e9, "peak": hbm_peak,
+             "unit": "GB/s", "algorithmic_bytes_per_voxel": 8, "kernel_ms": stage["ridge"]}
+    ridge["frac"] = ridge["achieved"] / hbm_peak
+
+    # ---- end to end: host buffers through the public call ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        del out
+        torch.cuda.empty_cache()
+        h_src = torch.empty((own_planes, ny, nx), dtype=torch.float32, pin_memory=True)
+        h_out = torch.empty((own_planes, ny, nx), dtype=torch.float32, pin_memory=True)
+        h_src.copy_(own)
+        if world == 1:
+            del own
+            torch.cuda.empty_cache()
+            src_np, out_np = h_src.numpy(), h_out.numpy()
+
+            def e2e_step():
+                # host pointers: the library stages H2D / D2H itself (the drop-in path)
+                ctx.membrane(src_np, SIGMA, RATIO, visfd_b200.DECREASING_EIVALS, TV_BEST, True, TV_SIGMA, 4, SQ2,
+                             out=out_np)
+        else:
+            d_out = torch.empty_like(own)
+
+            def e2e_step():
+                own.copy_(h_src, non_blocking=True)
+                pipe.run(own, out=d_out)
+                h_out.copy_(d_out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        e2e_step()
+        e2e_ms = timed(e2e_step, max(1, min(args.steps, 2)))
+        e2e = {"value": n_vox / (e2e_ms * 1e-3) / 1e9, "unit": "Gvoxel/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(4 * n_vox), "d2h_bytes_per_step": int(4 * n_vox),
+               "call": "visfd_cuda_membrane(host pointers)" if world == 1 else
+                       "pinned host slab -> H2D -> SlabMembrane.run -> D2H, per rank"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dt, cores, kind = cpu_reference_run(CPU_SAMPLE)
+        cpu = {"value": float(np.prod(CPU_SAMPLE)) / dt / 1e9, "unit": "Gvoxel/s", "cores": cores, "kind": kind,
+               "seconds": dt,
+               "sample": "%dx%dx%d crop of the synthetic workload with the same parameters (sigma 3, vote radius "
+                         "20, tv-best 0.05): one pipeline pass of the unmodified reference (OpenMP, all host "
+                         "threads)" % CPU_SAMPLE}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": n_vox / (ms_step * 1e-3) / 1e9, "unit": "Gvoxel/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(name, shape), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "roofline_gauss": gauss, "roofline_ridge": ridge, "cpu_baseline": cpu,
+                "stage_ms_rank0_last_step": stage, "halo_planes": pipe.plan.halo if world > 1 else 0}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

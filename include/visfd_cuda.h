@@ -68,10 +68,12 @@ void visfd_cuda_set_fast_gauss(visfd_ctx *ctx, int enabled);
 int visfd_cuda_trim(visfd_ctx *ctx);
 /* Number of kernel launches issued by ctx since creation (bench bookkeeping). */
 int64_t visfd_cuda_launch_count(visfd_ctx *ctx);
-/* Device milliseconds the most recent call spent in its named stage, measured
- * with CUDA events on the context's stream: "gauss", "ridge", "select", "compact",
- * "tv", "threshold", "h2d", "d2h".  Returns -1 for an unknown stage. */
+/* Device milliseconds spent in a named stage since the last visfd_cuda_reset_stage_ms,
+ * measured with CUDA events on the context's stream around the stage's kernels:
+ * "gauss", "ridge", "select", "compact", "tv", "threshold", "blob_scan", "h2d", "d2h".
+ * Returns -1 for a stage that has not run. */
 double visfd_cuda_stage_ms(visfd_ctx *ctx, const char *stage);
+void visfd_cuda_reset_stage_ms(visfd_ctx *ctx);
 
 /* ---- host-side parameter helpers (no GPU work) ----------------------------- */
 /* GenFilterGauss1D<float>(sigma, halfwidth): lib/visfd/filter1d.hpp:411-460.
@@ -241,14 +243,17 @@ void visfd_cuda_set_timing(visfd_ctx *ctx, int enabled);
 int64_t visfd_cuda_last_voter_count(visfd_ctx *ctx);
 /* Number of (receiver, voter) pairs the reference's TVReceiveStickVotes would evaluate
  * past its skip tests (feature.hpp:2251-2270) for this input: voters as above, receivers
- * = in-image voxels with mask_dst != 0 at squared distance <= hw^2.  The roofline's
- * FLOP count is 35 * pairs.  DEVICE or HOST pointers. */
+ * = voxels of planes [recv_z0, recv_z1) with mask_dst != 0 at squared distance <= hw^2.
+ * The roofline's FLOP count is 35 * pairs.  DEVICE or HOST pointers. */
 int visfd_cuda_tv_count_pairs(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
                               const float *saliency, float threshold, const float *mask_src,
-                              const float *mask_dst, int halfwidth, int64_t *pairs);
+                              const float *mask_dst, int halfwidth, int64_t recv_z0,
+                              int64_t recv_z1, int64_t *pairs);
 /* Sustained FP32 FMA throughput of the device in TFLOP/s (register-resident FFMA chains,
  * `ms` milliseconds of work): the measured denominator of the voting roofline. */
 int visfd_cuda_fp32_peak(visfd_ctx *ctx, double ms, double *tflops);
+/* The same with packed FFMA2 (fma.rn.f32x2) chains. */
+int visfd_cuda_fp32_peak_packed(visfd_ctx *ctx, double ms, double *tflops);
 
 /* ---- threshold / mask maps -------------------------------------------------------- */
 #define VISFD_THRESH_SINGLE 1 /* in > a ? outB : outA           handlers.cpp:1049-1053 */

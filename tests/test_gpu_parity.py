@@ -403,3 +403,36 @@ def test_blob_dog_masked_vs_oracle(ctx, oracle):
     for g, w in zip(got, want):
         g, w = sort_blobs(g), sort_blobs(w)
         assert g.shape == w.shape and np.array_equal(g, w)
+
+
+# ---- Z-slab stages (multi-GPU building blocks, emulated on one GPU) -----------------------------------
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_stages_reproduce_whole_volume(ctx, world):
+    """each emulated rank runs SlabMembrane's stages on its slab (own planes + raw-source
+    halo); stitched together the result equals the single-volume pipeline: the ridge
+    saliency bit for bit, the post-vote score to summation-order rounding"""
+    import torch
+    from visfd_b200.slab import make_plan, distributed_cut_threshold
+    shape = (60, 40, 48)
+    vol = synth.tomogram(shape, seed=17, n_shells=2)
+    sigma, ratio, tv_sigma = 1.5, 2.6482, 4.3
+    whole = ctx.membrane(vol, sigma, ratio, 1, 0.08, True, tv_sigma, 4, SQ2, want_saliency=True)
+    p = vb.MembraneParams(sigma, ratio, 1, 0.08, 1, tv_sigma, 4, SQ2)
+    gauss_hw = int(np.floor(np.float32(sigma) * np.float32(ratio)))
+    tv_hw = vb.tv_halfwidth(tv_sigma, SQ2)
+    dvol = torch.from_numpy(vol).cuda()
+    plans = [make_plan(shape[0], world, r, gauss_hw, tv_hw) for r in range(world)]
+    stage1 = []
+    for pl in plans:
+        sm, sal = ctx.ridge_saliency_slab(dvol[pl.slab[0]:pl.slab[1]].contiguous(), pl.slab[0], shape[0], sigma, ratio)
+        stage1.append((sm, sal))
+    # the global cut over the union of the ranks' OWN planes (what the all-reduce computes)
+    own_sal = torch.cat([stage1[r][1][plans[r].own_local[0]:plans[r].own_local[1]] for r in range(world)])
+    assert np.array_equal(own_sal.cpu().numpy() >= whole["threshold"], whole["hess_saliency"] != 0)
+    thr = distributed_cut_threshold(ctx, own_sal, 0.08)
+    assert np.float32(thr) == np.float32(whole["threshold"])
+    out = np.zeros(shape, np.float32)
+    for pl, (sm, sal) in zip(plans, stage1):
+        res, _ = ctx.vote_slab(sal, sm, pl.slab[0], shape[0], pl.own_local, pl.vote_local, thr, p)
+        out[pl.own[0]:pl.own[1]] = res.cpu().numpy()
+    assert rel_err(out, whole["out"], floor_frac=1e-2) <= 1e-5

@@ -55,6 +55,7 @@ def load_library():
     lib.visfd_cuda_key_to_float.restype = _f
     lib.visfd_cuda_set_timing.restype = None
     lib.visfd_cuda_set_fast_gauss.restype = None
+    lib.visfd_cuda_reset_stage_ms.restype = None
     lib.visfd_cuda_destroy.restype = None
     lib.visfd_cuda_gen_gauss1d.restype = None
     _lib = lib
@@ -166,6 +167,13 @@ class Context:
     def stage_ms(self, stage):
         return self.lib.visfd_cuda_stage_ms(self.h, stage.encode())
 
+    def reset_stage_ms(self):
+        self.lib.visfd_cuda_reset_stage_ms(self.h)
+
+    @staticmethod
+    def tv_halfwidth(sigma, cutoff_ratio):
+        return tv_halfwidth(sigma, cutoff_ratio)
+
     def set_timing(self, enabled):
         self.lib.visfd_cuda_set_timing(self.h, _i(int(enabled)))
 
@@ -179,17 +187,19 @@ class Context:
     def last_voter_count(self):
         return self.lib.visfd_cuda_last_voter_count(self.h)
 
-    def fp32_peak(self, ms=200.0):
+    def fp32_peak(self, ms=200.0, packed=False):
         t = _d()
-        self._ck(self.lib.visfd_cuda_fp32_peak(self.h, _d(ms), C.byref(t)))
+        fn = self.lib.visfd_cuda_fp32_peak_packed if packed else self.lib.visfd_cuda_fp32_peak
+        self._ck(fn(self.h, _d(ms), C.byref(t)))
         return t.value
 
-    def tv_count_pairs(self, saliency, threshold, halfwidth, mask_src=None, mask_dst=None):
+    def tv_count_pairs(self, saliency, threshold, halfwidth, mask_src=None, mask_dst=None, recv=None):
         s = _prep(saliency)
         n = _i64()
+        r0, r1 = (0, s.shape[0]) if recv is None else recv
         self._ck(self.lib.visfd_cuda_tv_count_pairs(self.h, *self._dims(s.shape), _ptr(s), _f(threshold),
                                                     _ptr(_prep(mask_src)), _ptr(_prep(mask_dst)),
-                                                    _i(halfwidth), C.byref(n)))
+                                                    _i(halfwidth), _i64(r0), _i64(r1), C.byref(n)))
         return n.value
 
     # ---- separable filters --------------------------------------------------------------

@@ -13,7 +13,7 @@ using namespace visfd_cuda;
   try {                                                        \
     VREQUIRE((ctx) != nullptr, "context is NULL");             \
     VCK(cudaSetDevice((ctx)->device));                         \
-    reset_stage_times(ctx);
+    drop_pending_stage_events(ctx);
 
 #define API_END(ctx)                                           \
     VCK(cudaStreamSynchronize((ctx)->stream));                 \
@@ -410,7 +410,7 @@ int64_t visfd_cuda_last_voter_count(visfd_ctx *ctx) { return ctx ? ctx->last_vot
 
 int visfd_cuda_tv_count_pairs(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *saliency,
                               float threshold, const float *mask_src, const float *mask_dst, int halfwidth,
-                              int64_t *pairs) {
+                              int64_t recv_z0, int64_t recv_z1, int64_t *pairs) {
   API_BEGIN(ctx)
   check_dims(nx, ny, nz);
   VREQUIRE(saliency && pairs, "NULL argument");
@@ -418,14 +418,23 @@ int visfd_cuda_tv_count_pairs(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz
   const bool host = on_host(saliency);
   Staged<float> s(ctx, saliency, N, Dir::In, host), ms(ctx, mask_src, N, Dir::In, host),
       md(ctx, mask_dst, N, Dir::In, host);
-  *pairs = tv_count_pairs_device(ctx, nx, ny, nz, s.get(), threshold, ms.get(), md.get(), halfwidth);
+  VREQUIRE(0 <= recv_z0 && recv_z0 <= recv_z1 && recv_z1 <= nz, "receiver planes outside the volume");
+  *pairs = tv_count_pairs_device(ctx, nx, ny, nz, s.get(), threshold, ms.get(), md.get(), halfwidth,
+                                 (int)recv_z0, (int)recv_z1);
   API_END(ctx)
 }
 
 int visfd_cuda_fp32_peak(visfd_ctx *ctx, double ms, double *tflops) {
   API_BEGIN(ctx)
   VREQUIRE(tflops, "NULL argument");
-  *tflops = fp32_peak_device(ctx, ms);
+  *tflops = fp32_peak_device(ctx, ms, false);
+  API_END(ctx)
+}
+
+int visfd_cuda_fp32_peak_packed(visfd_ctx *ctx, double ms, double *tflops) {
+  API_BEGIN(ctx)
+  VREQUIRE(tflops, "NULL argument");
+  *tflops = fp32_peak_device(ctx, ms, true);
   API_END(ctx)
 }
 

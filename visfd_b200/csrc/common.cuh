@@ -99,6 +99,7 @@ struct StageTimer {
   ~StageTimer();
 };
 void reset_stage_times(visfd_ctx *ctx);
+void drop_pending_stage_events(visfd_ctx *ctx);
 void resolve_stage_times(visfd_ctx *ctx);  // call after stream sync
 
 // A user array that may live on the host or on the device.

@@ -33,12 +33,16 @@ StageTimer::~StageTimer() {
   ctx->pending_events.push_back({name, a, b});
 }
 
-void reset_stage_times(visfd_ctx *ctx) {
+void drop_pending_stage_events(visfd_ctx *ctx) {
   for (auto &pe : ctx->pending_events) {
     cudaEventDestroy(pe.a);
     cudaEventDestroy(pe.b);
   }
   ctx->pending_events.clear();
+}
+
+void reset_stage_times(visfd_ctx *ctx) {
+  drop_pending_stage_events(ctx);
   ctx->stage_ms.clear();
 }
 
@@ -182,6 +186,10 @@ int64_t visfd_cuda_launch_count(visfd_ctx *ctx) { return ctx ? ctx->launches : -
 
 void visfd_cuda_set_fast_gauss(visfd_ctx *ctx, int enabled) {
   if (ctx) ctx->fast_gauss = enabled != 0;
+}
+
+void visfd_cuda_reset_stage_ms(visfd_ctx *ctx) {
+  if (ctx) reset_stage_times(ctx);
 }
 
 void visfd_cuda_set_timing(visfd_ctx *ctx, int enabled) {

@@ -91,7 +91,7 @@ void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *src, c
 
 // ---- util.cu ----------------------------------------------------------------------
 i64 tv_count_pairs_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *sal, float thr,
-                          const float *mask_src, const float *mask_dst, int hw);
-double fp32_peak_device(visfd_ctx *ctx, double ms_target);
+                          const float *mask_src, const float *mask_dst, int hw, int recv_z0, int recv_z1);
+double fp32_peak_device(visfd_ctx *ctx, double ms_target, bool packed);
 
 }  // namespace visfd_cuda

@@ -11,6 +11,7 @@ struct PairArgs {
   const float *sal, *mask_src, *mask_dst;
   float thr;
   int nx, ny, nz, hw;
+  int rz0, rz1;                       // receiver planes
   unsigned long long interior_count;  // lattice points with r^2 <= hw^2
 };
 
@@ -25,13 +26,13 @@ __global__ void __launch_bounds__(256) pair_count_kernel(PairArgs a, unsigned lo
     bool voter = (s >= a.thr) && s != 0.0f && !(a.mask_src && __ldg(a.mask_src + i) == 0.0f);
     if (voter) {
       const int hw = a.hw;
-      bool interior = ix >= hw && ix + hw < a.nx && iy >= hw && iy + hw < a.ny && iz >= hw && iz + hw < a.nz;
+      bool interior = ix >= hw && ix + hw < a.nx && iy >= hw && iy + hw < a.ny && iz - hw >= a.rz0 && iz + hw < a.rz1;
       if (interior && !a.mask_dst) {
         c = a.interior_count;
       } else {
         for (int dz = -hw; dz <= hw; dz++) {
           int z = iz + dz;
-          if (z < 0 || z >= a.nz) continue;
+          if (z < a.rz0 || z >= a.rz1) continue;
           for (int dy = -hw; dy <= hw; dy++) {
             int y = iy + dy;
             if (y < 0 || y >= a.ny) continue;
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(256) pair_count_kernel(PairArgs a, unsigned lo
 }
 
 i64 tv_count_pairs_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *sal, float thr,
-                          const float *mask_src, const float *mask_dst, int hw) {
+                          const float *mask_src, const float *mask_dst, int hw, int recv_z0, int recv_z1) {
   VREQUIRE(nx > 0 && ny > 0 && nz > 0 && nz <= 65535 && hw >= 0, "bad arguments to the pair count");
   unsigned long long V = 0;
   for (int dz = -hw; dz <= hw; dz++)
@@ -65,7 +66,7 @@ i64 tv_count_pairs_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *s
       for (int dx = -hw; dx <= hw; dx++) V += (dx * dx + dy * dy + dz * dz <= hw * hw);
   Scratch<unsigned long long> d(ctx, 1);
   VCK(cudaMemsetAsync(d.get(), 0, sizeof(unsigned long long), ctx->stream));
-  PairArgs a{sal, mask_src, mask_dst, thr, (int)nx, (int)ny, (int)nz, hw, V};
+  PairArgs a{sal, mask_src, mask_dst, thr, (int)nx, (int)ny, (int)nz, hw, recv_z0, recv_z1, V};
   dim3 grid(div_up(nx, 64), div_up(ny, 4), (unsigned)nz);
   pair_count_kernel<<<grid, 256, 0, ctx->stream>>>(a, d.get());
   VCK(cudaGetLastError());
@@ -92,19 +93,39 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, float a, flo
   if (s == 12345.678f) out[0] = s;  // keep the chains alive
 }
 
-double fp32_peak_device(visfd_ctx *ctx, double ms_target) {
+// the same with packed FFMA2 (fma.rn.f32x2, Blackwell): 2 FMAs per lane per instruction
+__global__ void __launch_bounds__(256) fp32x2_peak_kernel(float *out, float a, float b) {
+  float2 v[PEAK_CHAINS / 2];
+  const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+#pragma unroll
+  for (int k = 0; k < PEAK_CHAINS / 2; k++) v[k] = make_float2((float)(threadIdx.x + k), (float)k);
+  for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+    for (int k = 0; k < PEAK_CHAINS / 2; k++) v[k] = __ffma2_rn(v[k], a2, b2);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < PEAK_CHAINS / 2; k++) s += v[k].x + v[k].y;
+  if (s == 12345.678f) out[0] = s;
+}
+
+double fp32_peak_device(visfd_ctx *ctx, double ms_target, bool packed) {
   Scratch<float> d(ctx, 1);
   const int grid = ctx->sm_count * 8;
   cudaEvent_t e0, e1;
   VCK(cudaEventCreate(&e0));
   VCK(cudaEventCreate(&e1));
   // warm-up, then as many launches as fit the target time
-  for (int k = 0; k < 3; k++) fp32_peak_kernel<<<grid, 256, 0, ctx->stream>>>(d.get(), 0.999f, 0.001f);
+  auto launch = [&]() {
+    if (packed) fp32x2_peak_kernel<<<grid, 256, 0, ctx->stream>>>(d.get(), 0.999f, 0.001f);
+    else fp32_peak_kernel<<<grid, 256, 0, ctx->stream>>>(d.get(), 0.999f, 0.001f);
+  };
+  for (int k = 0; k < 3; k++) launch();
   VCK(cudaStreamSynchronize(ctx->stream));
   const double flop_per_launch = 2.0 * PEAK_CHAINS * (double)PEAK_ITERS * 256.0 * grid;
   int launches = std::max(1, (int)(ms_target * 1e-3 * 60e12 / flop_per_launch));
   VCK(cudaEventRecord(e0, ctx->stream));
-  for (int k = 0; k < launches; k++) fp32_peak_kernel<<<grid, 256, 0, ctx->stream>>>(d.get(), 0.999f, 0.001f);
+  for (int k = 0; k < launches; k++) launch();
   VCK(cudaEventRecord(e1, ctx->stream));
   VCK(cudaStreamSynchronize(ctx->stream));
   VCK(cudaGetLastError());
