@@ -33,10 +33,9 @@ namespace visfd_cuda {
 
 constexpr int BR = 8;            // brick edge
 constexpr int BR3 = BR * BR * BR;
-constexpr int TV_CHUNK = 512;    // voters per shared-memory stage
-constexpr int TV_THREADS = 256;
+constexpr int TV_THREADS = 256;   // 8 warps = one 8x8x8 receiver tile
+constexpr int TV_MIN_CTAS = 3;
 constexpr int TV_MAX_REACH = 7;  // bricks; hw <= 56
-constexpr int TV_MAX_ROWS = (2 * TV_MAX_REACH + 2) * (2 * TV_MAX_REACH + 1);
 constexpr int TV_MAX_SHELL = 512;
 
 int tv_halfwidth(float sigma, float cutoff_ratio) {
@@ -48,6 +47,7 @@ int tv_halfwidth(float sigma, float cutoff_ratio) {
 // ---------------------------------------------------------------------------------
 struct DecayInfo {
   float total;                      // sum of the un-normalised table (float, raster order)
+  int shell_total = 0, shell_kept = 0;  // lattice points with r^2 == hw^2: all / surviving the truncation
   std::vector<uint32_t> shell_keep; // packed |dx| | |dy|<<8 | |dz|<<16 of surviving shell points
 };
 
@@ -72,6 +72,10 @@ static DecayInfo decay_info(float sigma, int hw) {
         if (fabsf(h) < thr) h = 0.0f;
         total += h;
         int r2 = ix * ix + iy * iy + iz * iz;
+        if (r2 == hw2) {
+          info.shell_total++;
+          if (h != 0.0f) info.shell_kept++;
+        }
         if (r2 == hw2 && h != 0.0f && ix >= 0 && iy >= 0 && iz >= 0)
           info.shell_keep.push_back((uint32_t)ix | ((uint32_t)iy << 8) | ((uint32_t)iz << 16));
         // Lattice points strictly inside (outside) the shell are kept (dropped) by a
@@ -238,7 +242,7 @@ __device__ __forceinline__ void voter_direction(const DirSrc &d, int nx, int ny,
 
 __global__ void __launch_bounds__(BR3)
 voter_fill_kernel(VoterSrc v, DirSrc d, const uint32_t *__restrict__ off, float inv_total,
-                  float4 *__restrict__ va, float4 *__restrict__ vb) {
+                  float4 *__restrict__ va, float4 *__restrict__ vb, uint32_t *__restrict__ nonpos_flag) {
   __shared__ uint32_t wsum[BR3 / 32];
   const int b = blockIdx.x;
   const uint32_t o0 = off[b], o1 = off[b + 1];
@@ -257,7 +261,9 @@ voter_fill_kernel(VoterSrc v, DirSrc d, const uint32_t *__restrict__ off, float 
   for (int k = 0; k < w; k++) rank += wsum[k];
   float n[3];
   voter_direction(d, v.nx, v.ny, x, y, z, n);
-  va[o0 + rank] = make_float4((float)x, (float)y, (float)z, wt * inv_total);
+  const float wgt = wt * inv_total;
+  if (!(wgt > 0.0f)) *nonpos_flag = 1u;  // benign race: every writer stores the same value
+  va[o0 + rank] = make_float4((float)x, (float)y, (float)z, wgt);
   vb[o0 + rank] = make_float4(n[0], n[1], n[2], 0.0f);
 }
 
@@ -275,7 +281,10 @@ struct GatherArgs {
   i64 own_z0, own_z1;     // receiver planes (slab-local)
   int ntx, nty;           // receiver tiles in x,y
   int hw;
+  int row_cap;            // per-warp capacity of the row table
   float hw2;              // (float) hw*hw
+  float lim_in;           // pairs with r2 < lim_in get the full weight ...
+  float lim_pass;         // ... pairs with r2 in [lim_in, lim_pass) sit on the shell (SHELL kernels only)
   float neg_c;            // -log2(e)/sigma^2
   float half_exp;         // exponent/2, generic path
   const float *mask_dst;  // slab-indexed, or NULL
@@ -284,65 +293,27 @@ struct GatherArgs {
   int order, score_kind;
 };
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-__device__ __forceinline__ float fast_rsqrt(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ float fast_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
 __device__ __noinline__ float shell_weight(const uint32_t *shell, int n, float dx, float dy, float dz) {
   uint32_t key = (uint32_t)fabsf(dx) | ((uint32_t)fabsf(dy) << 8) | ((uint32_t)fabsf(dz) << 16);
   for (int k = 0; k < n; k++)
-    if (shell[k] == key) return 1.0f;
+    if (__ldg(shell + k) == key) return 1.0f;
   return 0.0f;
-}
-
-// EXPO: 2 or 4 = the reference's special cases (feature.hpp:2328-2339); 0 = pow()
-template <int EXPO, bool CURVES>
-__device__ __forceinline__ void vote_pair(float dx, float dy, float dz, float dxy2, float sxy,
-                                          const float4 &a, const float4 &n, const GatherArgs &g,
-                                          const uint32_t *shell, float T[6]) {
-  float r2 = fmaf(dz, dz, dxy2);
-  float sd = fmaf(dz, n.z, sxy);
-  float inv = fast_rsqrt(fmaxf(r2, 0.25f));  // r2 == 0: sd == 0, the vote is sal*decay*n n^T
-  float inv2 = inv * inv;
-  float e = fast_ex2(r2 * g.neg_c);
-  float sin2 = sd * sd * inv2;               // (r_hat . n)^2
-  float ang2 = CURVES ? sin2 : 1.0f - sin2;  // feature.hpp:2318-2326
-  float ang;
-  if (EXPO == 2) ang = ang2;
-  else if (EXPO == 4) ang = ang2 * ang2;
-  else ang = __powf(fmaxf(ang2, 0.0f), g.half_exp);
-  float w = a.w * e * ang;
-  w = (r2 < g.hw2) ? w : 0.0f;
-  if (r2 == g.hw2) w = a.w * e * ang * shell_weight(shell, g.n_shell, dx, dy, dz);
-  float t = (sd + sd) * inv2;
-  float vx, vy, vz;  // rotated normal: 2 s r_hat - n (surfaces) / n - 2 s r_hat (curves)
-  if (CURVES) {
-    vx = fmaf(-t, dx, n.x); vy = fmaf(-t, dy, n.y); vz = fmaf(-t, dz, n.z);
-  } else {
-    vx = fmaf(t, dx, -n.x); vy = fmaf(t, dy, -n.y); vz = fmaf(t, dz, -n.z);
-  }
-  float wx = w * vx, wy = w * vy, wz = w * vz;
-  T[0] = fmaf(wx, vx, T[0]);
-  T[1] = fmaf(wy, vy, T[1]);
-  T[2] = fmaf(wz, vz, T[2]);
-  T[3] = fmaf(wx, vy, T[3]);
-  T[4] = fmaf(wy, vz, T[4]);
-  T[5] = fmaf(wx, vz, T[5]);
 }
 
 __device__ __forceinline__ int axis_gap(int lo_a, int hi_a, int lo_b, int hi_b) {
@@ -350,115 +321,263 @@ __device__ __forceinline__ int axis_gap(int lo_a, int hi_a, int lo_b, int hi_b) 
   return max(0, max(lo_b - hi_a, lo_a - hi_b));
 }
 
-template <int EXPO, bool CURVES>
-__global__ void __launch_bounds__(TV_THREADS, 2) tv_gather_kernel(GatherArgs g) {
-  __shared__ __align__(16) float4 s_a[2][TV_CHUNK];
-  __shared__ __align__(16) float4 s_b[2][TV_CHUNK];
-  __shared__ uint32_t s_row_start[TV_MAX_ROWS];
-  __shared__ uint32_t s_row_prefix[TV_MAX_ROWS + 1];
-  __shared__ uint32_t s_shell[TV_MAX_SHELL];
+// One queued voter (48 B, read by the whole warp as three broadcast LDS.128).  The two
+// receivers of a lane share x and y, so the x/y terms of every dot product are scalar
+// and only the z terms are packed pairs; the pairs are stored duplicated so that they
+// come out of the load as aligned register pairs.
+struct __align__(16) QEntry {
+  float4 a;  // {-x, -y, nx, ny}
+  float4 b;  // {nx/2, ny/2, nz, nz/2}
+  float4 c;  // {-z, -z, lw, lw}   lw: see TV_SQRTW below
+};
 
+constexpr int TV_QCAP = 64;    // ring capacity per class (entries); drained 32 at a time
+constexpr int TV_DRAIN = 32;
+constexpr float TV_R2_EPS = 1e-30f;  // keeps 1/r^2 finite for the self vote (r = 0, d.n = 0)
+
+__device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }  // FFMA2 takes scalar (.F32) operands
+
+// The vote of one voter on the two receivers (x, y, z) and (x, y, z+1) of a lane.
+// With r = receiver - voter, r2 = |r|^2, d = r.n, q = d/r2:  sin^2 = q*d (cos^2 = 1 - q*d),
+// rotated normal v = n - 2 q r (feature.hpp:2341-2351; its sign does not matter for
+// v v^T, so surfaces and curves share it).  We accumulate with h = v/2 = n/2 - q r and
+// fold the factor 4 into the weight.
+//   SQRTW (exponent 4, all weights > 0): weight*decay*ang^2*4 = (sE*ang)^2 with
+//     sE = exp2(r2*neg_c/2 + lw), lw = log2(4*weight)/2; T += (sE*ang*h)(sE*ang*h)^T
+//   otherwise: w = decay*ang^(e/2)*weight*4,  T += (w h) h^T
+// BOUNDARY: the voter's support sphere cuts through the warp's patch: pairs outside the
+// support get weight 0.  Lattice points exactly on the shell r2 == hw^2 are kept or
+// dropped by float rounding in the reference's table (filter3d.hpp:546-601); the host
+// evaluates that table: all kept (every parameter set we have seen) or all dropped is
+// folded into lim_in = hw^2 +- 0.5; a mixed shell runs the SHELL kernels, which look
+// each on-shell pair up in the list of kept points.
+template <int EXPO, bool CURVES, bool POSW, bool BOUNDARY, bool SHELL>
+__device__ __forceinline__ void vote(const QEntry *q, float fx, float fy, float2 fz,
+                                     const GatherArgs &g, float2 negc, float2 T[6]) {
+  constexpr bool SQRTW = (EXPO == 4) && POSW;
+  const float4 ea = q->a, eb = q->b, ec = q->c;
+  const float rx = fx + ea.x, ry = fy + ea.y;
+  const float rxy2 = fmaf(ry, ry, fmaf(rx, rx, TV_R2_EPS));
+  const float dxy = fmaf(ry, ea.w, rx * ea.z);
+  const float2 rz = __fadd2_rn(fz, make_float2(ec.x, ec.y));
+  const float2 r2 = __ffma2_rn(rz, rz, bc(rxy2));
+  const float2 d = __ffma2_rn(rz, bc(eb.z), bc(dxy));
+  float2 ee;
+  if (POSW) {
+    const float2 arg = __ffma2_rn(r2, negc, make_float2(ec.z, ec.w));
+    ee = make_float2(fast_ex2(arg.x), fast_ex2(arg.y));
+  } else {
+    const float2 arg = __fmul2_rn(r2, negc);
+    ee = __fmul2_rn(make_float2(fast_ex2(arg.x), fast_ex2(arg.y)), make_float2(ec.z, ec.w));
+  }
+  const float2 ninv = make_float2(fast_rcp(-r2.x), fast_rcp(-r2.y));
+  const float2 qn = __fmul2_rn(d, ninv);  // -q
+  float2 ang2;                             // cos^2 (surfaces) / -sin^2 (curves)
+  if (CURVES) ang2 = __fmul2_rn(qn, d);
+  else ang2 = __ffma2_rn(qn, d, make_float2(1.0f, 1.0f));
+  float2 w;
+  if (SQRTW) {
+    w = __fmul2_rn(ee, ang2);              // sign irrelevant: it is squared below
+  } else {
+    if (CURVES) ang2 = make_float2(-ang2.x, -ang2.y);
+    float2 ang;
+    if (EXPO == 2) ang = ang2;
+    else if (EXPO == 4) ang = __fmul2_rn(ang2, ang2);
+    else ang = make_float2(fast_ex2(g.half_exp * fast_lg2(fmaxf(ang2.x, 0.0f))),
+                           fast_ex2(g.half_exp * fast_lg2(fmaxf(ang2.y, 0.0f))));
+    w = __fmul2_rn(ee, ang);
+  }
+  if (BOUNDARY) {
+    const float2 wfull = w;
+    w.x = (r2.x < g.lim_in) ? w.x : 0.0f;
+    w.y = (r2.y < g.lim_in) ? w.y : 0.0f;
+    if (SHELL) {
+      const bool sx = r2.x >= g.lim_in && r2.x < g.lim_pass, sy = r2.y >= g.lim_in && r2.y < g.lim_pass;
+      if (__any_sync(0xffffffffu, sx || sy)) {
+        if (sx) w.x = wfull.x * shell_weight(g.shell, g.n_shell, rx, ry, rz.x);
+        if (sy) w.y = wfull.y * shell_weight(g.shell, g.n_shell, rx, ry, rz.y);
+      }
+    }
+  }
+  const float2 hx = __ffma2_rn(qn, bc(rx), bc(eb.x));
+  const float2 hy = __ffma2_rn(qn, bc(ry), bc(eb.y));
+  const float2 hz = __ffma2_rn(qn, rz, bc(eb.w));
+  const float2 wx = __fmul2_rn(w, hx), wy = __fmul2_rn(w, hy), wz = __fmul2_rn(w, hz);
+  if (SQRTW) {
+    T[0] = __ffma2_rn(wx, wx, T[0]);
+    T[1] = __ffma2_rn(wy, wy, T[1]);
+    T[2] = __ffma2_rn(wz, wz, T[2]);
+    T[3] = __ffma2_rn(wx, wy, T[3]);
+    T[4] = __ffma2_rn(wy, wz, T[4]);
+    T[5] = __ffma2_rn(wx, wz, T[5]);
+  } else {
+    T[0] = __ffma2_rn(wx, hx, T[0]);
+    T[1] = __ffma2_rn(wy, hy, T[1]);
+    T[2] = __ffma2_rn(wz, hz, T[2]);
+    T[3] = __ffma2_rn(wx, hy, T[3]);
+    T[4] = __ffma2_rn(wy, hz, T[4]);
+    T[5] = __ffma2_rn(wx, hz, T[5]);
+  }
+}
+
+// n consecutive entries (n even).  A ring's head is always 0 or TV_DRAIN and at most
+// TV_DRAIN entries are drained at a time, so a drain never wraps.
+template <int EXPO, bool CURVES, bool POSW, bool BOUNDARY, bool SHELL>
+__device__ __forceinline__ void drain(const QEntry *q, int n, float fx, float fy, float2 fz,
+                                      const GatherArgs &g, float2 negc, float2 T[6]) {
+  const QEntry *end = q + n;
+#pragma unroll 1
+  for (; q != end; q += 2) {
+    vote<EXPO, CURVES, POSW, BOUNDARY, SHELL>(q, fx, fy, fz, g, negc, T);
+    vote<EXPO, CURVES, POSW, BOUNDARY, SHELL>(q + 1, fx, fy, fz, g, negc, T);
+  }
+}
+
+// One WARP per 4x4x4 receiver patch (lane = (x, y, z/2): two z-adjacent receivers, 12
+// accumulators in registers as six packed pairs); the 8 warps of a CTA cover an 8x8x8
+// tile but never synchronise with each other.  A warp
+//   1. builds the table of brick rows (contiguous ranges of the brick-ordered voter
+//      list) whose bricks can reach its patch,
+//   2. streams them 32 candidates at a time -- one candidate per lane, loaded straight
+//      from L1/L2 one batch ahead -- and classifies each against the patch: out of
+//      reach / INNER (all 64 receivers strictly inside the support sphere) / BOUNDARY,
+//   3. appends the survivors to two warp-private shared-memory rings and, whenever a ring
+//      holds 32, drains them: every lane evaluates the voter (broadcast LDS) on its two
+//      receivers.  INNER votes need no support test at all.
+template <int EXPO, bool CURVES, bool POSW, bool SHELL>
+__global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(GatherArgs g) {
+  extern __shared__ __align__(16) unsigned char tv_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t per_warp = 2 * TV_QCAP * sizeof(QEntry) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t);
+  unsigned char *mine = tv_smem + warp * ((per_warp + 15) & ~(size_t)15);
+  QEntry *ring_i = reinterpret_cast<QEntry *>(mine);
+  QEntry *ring_b = ring_i + TV_QCAP;
+  uint32_t *row_start = reinterpret_cast<uint32_t *>(ring_b + TV_QCAP);
+  uint32_t *row_pref = row_start + g.row_cap;  // [row_cap + 1]
+
   const int tile = blockIdx.x;
   const int tx = tile % g.ntx, ty = (tile / g.ntx) % g.nty, tz = tile / (g.ntx * g.nty);
-  const int X0 = tx * BR, Y0 = ty * BR;
-  const i64 Z0 = g.own_z0 + (i64)tz * BR;
-  const int Z1 = (int)min((i64)(Z0 + BR - 1), g.own_z1 - 1);  // last receiver plane of the tile
+  const int px = tx * BR + (warp & 1) * 4, py = ty * BR + ((warp >> 1) & 1) * 4;
+  const int pz = (int)g.own_z0 + tz * BR + (warp >> 2) * 4;
+  if (px >= g.nx || py >= g.ny || pz >= g.own_z1) return;  // whole warp: no receivers
+  const int pz_hi = (int)min((i64)pz + 3, g.own_z1 - 1), py_hi = min(py + 3, g.ny - 1), px_hi = min(px + 3, g.nx - 1);
 
-  // ---- neighbourhood rows --------------------------------------------------------
-  const int bz_lo = (int)max((i64)0, (Z0 - g.hw) >> 3);
-  const int bz_hi = (int)min((i64)g.nbz - 1, (i64)(Z1 + g.hw) >> 3);
-  const int by_lo = max(0, (Y0 - g.hw) >> 3);
-  const int by_hi = min(g.nby - 1, (Y0 + BR - 1 + g.hw) >> 3);
+  // ---- 1. brick rows that can reach the patch ----------------------------------------
+  const int bz_lo = max(0, (pz - g.hw) >> 3), bz_hi = min(g.nbz - 1, (pz_hi + g.hw) >> 3);
+  const int by_lo = max(0, (py - g.hw) >> 3), by_hi = min(g.nby - 1, (py_hi + g.hw) >> 3);
   const int nry = by_hi - by_lo + 1;
-  const int nrows = max(0, (bz_hi - bz_lo + 1)) * nry;
-  for (int r = tid; r < nrows; r += TV_THREADS) {
-    int bz = bz_lo + r / nry, by = by_lo + r % nry;
-    int dz = axis_gap((int)Z0, Z1, bz * BR, bz * BR + BR - 1);
-    int dy = axis_gap(Y0, Y0 + BR - 1, by * BR, by * BR + BR - 1);
-    int rem = g.hw * g.hw - dz * dz - dy * dy;
+  const int nrows = (bz_hi - bz_lo + 1) * nry;  // <= row_cap by construction
+  uint32_t carry = 0;
+  for (int r0 = 0; r0 < nrows; r0 += 32) {
+    const int r = r0 + lane;
     uint32_t start = 0, len = 0;
-    if (rem >= 0) {
-      int d = (int)floorf(sqrtf((float)rem));
-      while ((d + 1) * (d + 1) <= rem) d++;
-      while (d * d > rem) d--;
-      int bx_lo = max(0, (X0 - d) >> 3), bx_hi = min(g.nbx - 1, (X0 + BR - 1 + d) >> 3);
-      i64 rb = ((i64)bz * g.nby + by) * g.nbx;
-      start = g.off[rb + bx_lo];
-      len = g.off[rb + bx_hi + 1] - start;
+    if (r < nrows) {
+      const int bz = bz_lo + r / nry, by = by_lo + r % nry;
+      const int dz = axis_gap(pz, pz_hi, bz * BR, bz * BR + BR - 1);
+      const int dy = axis_gap(py, py_hi, by * BR, by * BR + BR - 1);
+      const int rem = g.hw * g.hw - dz * dz - dy * dy;
+      if (rem >= 0) {
+        int d = (int)floorf(sqrtf((float)rem));
+        while ((d + 1) * (d + 1) <= rem) d++;
+        while (d * d > rem) d--;
+        const int bx_lo = max(0, (px - d) >> 3), bx_hi = min(g.nbx - 1, (px_hi + d) >> 3);
+        const i64 rb = ((i64)bz * g.nby + by) * g.nbx;
+        start = __ldg(g.off + rb + bx_lo);
+        len = __ldg(g.off + rb + bx_hi + 1) - start;
+      }
     }
-    s_row_start[r] = start;
-    s_row_prefix[r + 1] = len;
-  }
-  for (int k = tid; k < g.n_shell; k += TV_THREADS) s_shell[k] = g.shell[k];
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t acc = 0;
-    s_row_prefix[0] = 0;
-    for (int r = 0; r < nrows; r++) {
-      acc += s_row_prefix[r + 1];
-      s_row_prefix[r + 1] = acc;
-    }
-  }
-  __syncthreads();
-  const uint32_t total = s_row_prefix[nrows];
-  const int nchunks = (int)((total + TV_CHUNK - 1) / TV_CHUNK);
-
-  // ---- receivers of this lane ------------------------------------------------------
-  const int px = X0 + (warp & 1) * 4, py = Y0 + ((warp >> 1) & 1) * 4;
-  const int pz = (int)Z0 + (warp >> 2) * 4;
-  const int ix = px + (lane & 3), iy = py + ((lane >> 2) & 3), iz = pz + (lane >> 4) * 2;
-  const float rx = (float)ix, ry = (float)iy, rz0 = (float)iz, rz1 = (float)(iz + 1);
-  const float pcx = px + 1.5f, pcy = py + 1.5f, pcz = pz + 1.5f;
-  float T0[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, T1[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-
-  // ---- stream the voter ranges ---------------------------------------------------------
-  int cur_row = 0;  // per-thread cursor into the row table (flat indices only grow)
-  auto issue = [&](int c) {
-    const int buf = c & 1;
-    const uint32_t base = (uint32_t)c * TV_CHUNK;
+    uint32_t incl = len;
 #pragma unroll
-    for (int k = 0; k < TV_CHUNK / TV_THREADS; k++) {
-      uint32_t e = base + tid + k * TV_THREADS;
-      if (e < total) {
-        while (e >= s_row_prefix[cur_row + 1]) cur_row++;
-        uint32_t gi = s_row_start[cur_row] + (e - s_row_prefix[cur_row]);
-        cp_async16(&s_a[buf][e - base], g.va + gi);
-        cp_async16(&s_b[buf][e - base], g.vb + gi);
-      }
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
     }
-    cp_async_commit();
+    if (r < nrows) {
+      row_start[r] = start;
+      row_pref[r] = carry + incl - len;
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) row_pref[nrows] = carry;
+  __syncwarp();
+  const uint32_t total = carry;
+
+  // ---- receivers of this lane: (ix, iy, iz) and (ix, iy, iz+1) ------------------------
+  const int ix = px + (lane & 3), iy = py + ((lane >> 2) & 3), iz = pz + (lane >> 4) * 2;
+  const float fx = (float)ix, fy = (float)iy;
+  const float2 fz = make_float2((float)iz, (float)(iz + 1));
+  const float pcx = px + 1.5f, pcy = py + 1.5f, pcz = pz + 1.5f;
+  constexpr bool SQRTW = (EXPO == 4) && POSW;
+  const float nc = SQRTW ? 0.5f * g.neg_c : g.neg_c;
+  const float2 negc = make_float2(nc, nc);
+  float2 T[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) T[k] = make_float2(0.0f, 0.0f);
+
+  // ---- 2./3. stream, classify, vote -----------------------------------------------------
+  int cur_row = 0;  // per-lane cursor into the row table (flat indices only grow)
+  auto fetch = [&](uint32_t e, float4 &a, float4 &b) {
+    if (e < total) {
+      while (e >= row_pref[cur_row + 1]) cur_row++;
+      const uint32_t gi = row_start[cur_row] + (e - row_pref[cur_row]);
+      a = __ldg(g.va + gi);
+      b = __ldg(g.vb + gi);
+    }
   };
-  if (nchunks > 0) issue(0);
-  for (int c = 0; c < nchunks; c++) {
-    if (c + 1 < nchunks) issue(c + 1); else cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    const int buf = c & 1;
-    const int cn = (int)min((uint32_t)TV_CHUNK, total - (uint32_t)c * TV_CHUNK);
-    for (int base = 0; base < cn; base += 32) {
-      bool pass = false;
-      if (base + lane < cn) {
-        float4 a = s_a[buf][base + lane];
-        float ddx = fmaxf(fabsf(a.x - pcx) - 1.5f, 0.0f);
-        float ddy = fmaxf(fabsf(a.y - pcy) - 1.5f, 0.0f);
-        float ddz = fmaxf(fabsf(a.z - pcz) - 1.5f, 0.0f);
-        pass = fmaf(ddx, ddx, fmaf(ddy, ddy, ddz * ddz)) <= g.hw2;
-      }
-      unsigned m = __ballot_sync(0xffffffffu, pass);
-      while (m) {
-        int j = base + __ffs(m) - 1;
-        m &= m - 1;
-        const float4 a = s_a[buf][j];
-        const float4 n = s_b[buf][j];
-        float dx = rx - a.x, dy = ry - a.y;
-        float dxy2 = fmaf(dx, dx, dy * dy);
-        float sxy = fmaf(dx, n.x, dy * n.y);
-        vote_pair<EXPO, CURVES>(dx, dy, rz0 - a.z, dxy2, sxy, a, n, g, s_shell, T0);
-        vote_pair<EXPO, CURVES>(dx, dy, rz1 - a.z, dxy2, sxy, a, n, g, s_shell, T1);
-      }
+  auto put = [&](QEntry *slot, const float4 &a, const float4 &n) {
+    float lw;
+    if (SQRTW) lw = fmaf(0.5f, fast_lg2(a.w), 1.0f);      // log2(4 w)/2
+    else if (POSW) lw = fast_lg2(a.w) + 2.0f;             // log2(4 w)
+    else lw = 4.0f * a.w;
+    slot->a = make_float4(-a.x, -a.y, n.x, n.y);
+    slot->b = make_float4(0.5f * n.x, 0.5f * n.y, n.z, 0.5f * n.z);
+    slot->c = make_float4(-a.z, -a.z, lw, lw);
+  };
+  int head_i = 0, cnt_i = 0, head_b = 0, cnt_b = 0;
+  float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+  fetch(lane, na, nb);
+  for (uint32_t base = 0; base < total; base += 32) {
+    const float4 a = na, b = nb;
+    const bool valid = base + lane < total;
+    fetch(base + 32 + lane, na, nb);
+    const float ax = fabsf(a.x - pcx), ay = fabsf(a.y - pcy), az = fabsf(a.z - pcz);
+    const float gx = fmaxf(ax - 1.5f, 0.0f), gy = fmaxf(ay - 1.5f, 0.0f), gz = fmaxf(az - 1.5f, 0.0f);
+    const float hx = ax + 1.5f, hy = ay + 1.5f, hz = az + 1.5f;
+    const float dmin2 = fmaf(gx, gx, fmaf(gy, gy, gz * gz));
+    const float dmax2 = fmaf(hx, hx, fmaf(hy, hy, hz * hz));
+    const bool pass = valid && dmin2 < g.lim_pass;
+    const bool inner = pass && dmax2 < g.lim_in;
+    const unsigned mi = __ballot_sync(0xffffffffu, inner);
+    const unsigned mb = __ballot_sync(0xffffffffu, pass && !inner);
+    const unsigned below = (1u << lane) - 1u;
+    if (inner) put(ring_i + ((head_i + cnt_i + __popc(mi & below)) & (TV_QCAP - 1)), a, b);
+    else if (pass) put(ring_b + ((head_b + cnt_b + __popc(mb & below)) & (TV_QCAP - 1)), a, b);
+    cnt_i += __popc(mi);
+    cnt_b += __popc(mb);
+    __syncwarp();
+    if (cnt_i >= TV_DRAIN) {
+      drain<EXPO, CURVES, POSW, false, false>(ring_i + head_i, TV_DRAIN, fx, fy, fz, g, negc, T);
+      head_i = (head_i + TV_DRAIN) & (TV_QCAP - 1);
+      cnt_i -= TV_DRAIN;
     }
-    __syncthreads();
+    if (cnt_b >= TV_DRAIN) {
+      drain<EXPO, CURVES, POSW, true, SHELL>(ring_b + head_b, TV_DRAIN, fx, fy, fz, g, negc, T);
+      head_b = (head_b + TV_DRAIN) & (TV_QCAP - 1);
+      cnt_b -= TV_DRAIN;
+    }
+    __syncwarp();
+  }
+  // leftovers, padded to an even count with a zero-weight voter
+  {
+    const float4 far = make_float4(-1.0e4f, -1.0e4f, -1.0e4f, 0.0f);  // lg2(0) = -inf, ex2(-inf) = 0
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane == 0) {
+      if (cnt_i & 1) put(ring_i + ((head_i + cnt_i) & (TV_QCAP - 1)), far, zero);
+      if (cnt_b & 1) put(ring_b + ((head_b + cnt_b) & (TV_QCAP - 1)), far, zero);
+    }
+    __syncwarp();
+    drain<EXPO, CURVES, POSW, false, false>(ring_i + head_i, (cnt_i + 1) & ~1, fx, fy, fz, g, negc, T);
+    drain<EXPO, CURVES, POSW, true, SHELL>(ring_b + head_b, (cnt_b + 1) & ~1, fx, fy, fz, g, negc, T);
   }
 
   // ---- epilogue ---------------------------------------------------------------------
@@ -467,21 +586,23 @@ __global__ void __launch_bounds__(TV_THREADS, 2) tv_gather_kernel(GatherArgs g) 
     for (int r = 0; r < 2; r++) {
       const i64 z = iz + r;
       if (z >= g.own_z1) break;
-      const float *T = r ? T1 : T0;
+      float Tr[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) Tr[k] = r ? T[k].y : T[k].x;
       const i64 slab_i = (z * g.ny + iy) * (i64)g.nx + ix;
       const i64 out_i = ((z - g.own_z0) * g.ny + iy) * (i64)g.nx + ix;
       const bool masked = g.mask_dst && __ldg(g.mask_dst + slab_i) == 0.0f;  // feature.hpp:2002-2003
       if (g.tensor) {
         float *o = g.tensor + 6 * out_i;
 #pragma unroll
-        for (int k = 0; k < 6; k++) o[k] = masked ? 0.0f : T[k];
+        for (int k = 0; k < 6; k++) o[k] = masked ? 0.0f : Tr[k];
       }
       if (g.score) {
         float sc = 0.0f;
         if (!masked) {
-          Sym3d m = {T[0], T[1], T[2], T[3], T[4], T[5]};
+          Sym3d mm = {Tr[0], Tr[1], Tr[2], Tr[3], Tr[4], Tr[5]};
           double ev[3];
-          sym3_eigenvalues(m, g.order, ev);
+          sym3_eigenvalues(mm, g.order, ev);
           sc = score_from_eivals(ev, g.score_kind, 1);
         }
         g.score[out_i] = sc;
@@ -516,8 +637,8 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
 
   Scratch<uint32_t> counts(ctx, n_bricks), off(ctx, n_bricks + 1);
   const i64 n_scan_blocks = (n_bricks + SCAN_B - 1) / SCAN_B;
-  Scratch<uint32_t> sums(ctx, n_scan_blocks + 1);
-  uint32_t n_voters = 0;
+  Scratch<uint32_t> sums(ctx, n_scan_blocks + 2);   // block sums, [n] = total, [n+1] = non-positive-weight flag
+  uint32_t n_voters = 0, nonpos = 0;
   Scratch<float4> va, vb;
   {
     StageTimer t(ctx, "compact");
@@ -538,10 +659,15 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
     vb.reset(ctx, std::max<size_t>(n_voters, 1));
     if (n_voters > 0) {
       DirSrc ds{direction, smoothed, ridge_sigma, eival_order, z_offset, nz_global};
+      VCK(cudaMemsetAsync(sums.get() + n_scan_blocks + 1, 0, sizeof(uint32_t), ctx->stream));
       voter_fill_kernel<<<(unsigned)n_bricks, BR3, 0, ctx->stream>>>(vs, ds, off.get(), 1.0f / info.total,
-                                                                     va.get(), vb.get());
+                                                                     va.get(), vb.get(),
+                                                                     sums.get() + n_scan_blocks + 1);
       VCK(cudaGetLastError());
       ctx->count_launch();
+      VCK(cudaMemcpyAsync(&nonpos, sums.get() + n_scan_blocks + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+      VCK(cudaStreamSynchronize(ctx->stream));
     }
   }
   ctx->last_voters = n_voters;
@@ -559,6 +685,12 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   g.own_z0 = own_z0; g.own_z1 = own_z1;
   g.ntx = nbx; g.nty = nby;
   g.hw = hw; g.hw2 = (float)(hw * hw);
+  { const int per_axis = ((2 * hw + 3) >> 3) + 2; g.row_cap = per_axis * per_axis; }
+  // lattice points on the shell r2 == hw^2: all kept / all dropped / mixed (see vote())
+  const bool mixed_shell = info.shell_total != 0 && info.shell_kept != 0 && info.shell_kept != info.shell_total;
+  const bool shell_in = info.shell_total != 0 && info.shell_kept == info.shell_total;
+  g.lim_in = g.hw2 + ((shell_in && !mixed_shell) ? 0.5f : -0.5f);
+  g.lim_pass = g.hw2 + ((shell_in || mixed_shell) ? 0.5f : -0.5f);
   g.neg_c = (float)(-1.4426950408889634 / ((double)p.sigma * (double)p.sigma));
   g.half_exp = 0.5f * (float)p.exponent;
   g.mask_dst = mask_dst; g.tensor = tensor; g.score = score;
@@ -569,15 +701,33 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   {
     StageTimer t(ctx, "tv");
     const unsigned grid = (unsigned)n_tiles;
+    // POSW: all voter weights > 0 (always true for the planar ridge score), so log2(weight)
+    // rides in the decay exponent
+    const size_t per_warp = (2 * TV_QCAP * sizeof(QEntry) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t) + 15) & ~(size_t)15;
+    const size_t smem = (TV_THREADS / 32) * per_warp;
+#define TV_LAUNCH1(E, C, P, S)                                                                            \
+    do {                                                                                                  \
+      VCK(cudaFuncSetAttribute(tv_gather_kernel<E, C, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               (int)smem));                                                               \
+      tv_gather_kernel<E, C, P, S><<<grid, TV_THREADS, smem, ctx->stream>>>(g);                           \
+    } while (0)
+#define TV_LAUNCH(E, C)                                   \
+    do {                                                  \
+      if (mixed_shell) TV_LAUNCH1(E, C, false, true);     \
+      else if (nonpos) TV_LAUNCH1(E, C, false, false);    \
+      else TV_LAUNCH1(E, C, true, false);                 \
+    } while (0)
     if (p.curves) {
-      if (p.exponent == 2) tv_gather_kernel<2, true><<<grid, TV_THREADS, 0, ctx->stream>>>(g);
-      else if (p.exponent == 4) tv_gather_kernel<4, true><<<grid, TV_THREADS, 0, ctx->stream>>>(g);
-      else tv_gather_kernel<0, true><<<grid, TV_THREADS, 0, ctx->stream>>>(g);
+      if (p.exponent == 2) TV_LAUNCH(2, true);
+      else if (p.exponent == 4) TV_LAUNCH(4, true);
+      else TV_LAUNCH(0, true);
     } else {
-      if (p.exponent == 2) tv_gather_kernel<2, false><<<grid, TV_THREADS, 0, ctx->stream>>>(g);
-      else if (p.exponent == 4) tv_gather_kernel<4, false><<<grid, TV_THREADS, 0, ctx->stream>>>(g);
-      else tv_gather_kernel<0, false><<<grid, TV_THREADS, 0, ctx->stream>>>(g);
+      if (p.exponent == 2) TV_LAUNCH(2, false);
+      else if (p.exponent == 4) TV_LAUNCH(4, false);
+      else TV_LAUNCH(0, false);
     }
+#undef TV_LAUNCH
+#undef TV_LAUNCH1
     VCK(cudaGetLastError());
     ctx->count_launch();
   }
