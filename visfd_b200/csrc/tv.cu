@@ -194,6 +194,13 @@ scan_add_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ sums, i
   if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
 }
 
+// One voter as the gather kernel consumes it (48 B; copied verbatim into shared memory).
+struct __align__(16) VoterRec {
+  float4 a;  // {-x, -y, -z, log2(4w)/2}
+  float4 b;  // {nx, ny, nz, log2(4w)}
+  float4 c;  // {nx/2, ny/2, nz/2, 4w}       w = saliency * mask weight / table total
+};
+
 struct DirSrc {
   const float *direction;  // N*3, or NULL
   const float *smoothed;   // used when direction == NULL
@@ -242,7 +249,7 @@ __device__ __forceinline__ void voter_direction(const DirSrc &d, int nx, int ny,
 
 __global__ void __launch_bounds__(BR3)
 voter_fill_kernel(VoterSrc v, DirSrc d, const uint32_t *__restrict__ off, float inv_total,
-                  float4 *__restrict__ va, float4 *__restrict__ vb, uint32_t *__restrict__ nonpos_flag) {
+                  VoterRec *__restrict__ rec, uint32_t *__restrict__ nonpos_flag) {
   __shared__ uint32_t wsum[BR3 / 32];
   const int b = blockIdx.x;
   const uint32_t o0 = off[b], o1 = off[b + 1];
@@ -263,15 +270,20 @@ voter_fill_kernel(VoterSrc v, DirSrc d, const uint32_t *__restrict__ off, float 
   voter_direction(d, v.nx, v.ny, x, y, z, n);
   const float wgt = wt * inv_total;
   if (!(wgt > 0.0f)) *nonpos_flag = 1u;  // benign race: every writer stores the same value
-  va[o0 + rank] = make_float4((float)x, (float)y, (float)z, wgt);
-  vb[o0 + rank] = make_float4(n[0], n[1], n[2], 0.0f);
+  // the three forms of the weight the gather kernels fold into their arithmetic (vote())
+  const float w4 = 4.0f * wgt, l4 = log2f(w4);
+  VoterRec r;
+  r.a = make_float4(-(float)x, -(float)y, -(float)z, 0.5f * l4);
+  r.b = make_float4(n[0], n[1], n[2], l4);
+  r.c = make_float4(0.5f * n[0], 0.5f * n[1], 0.5f * n[2], w4);
+  rec[o0 + rank] = r;
 }
 
 // ---------------------------------------------------------------------------------
 // gather
 // ---------------------------------------------------------------------------------
 struct GatherArgs {
-  const float4 *va, *vb;
+  const VoterRec *rec;
   const uint32_t *off;
   const uint32_t *shell;  // device copy of DecayInfo::shell_keep
   int n_shell;
@@ -292,6 +304,14 @@ struct GatherArgs {
   float *score;           // own-planes-indexed, or NULL
   int order, score_kind;
 };
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ float fast_ex2(float x) {
   float y;
@@ -321,19 +341,9 @@ __device__ __forceinline__ int axis_gap(int lo_a, int hi_a, int lo_b, int hi_b) 
   return max(0, max(lo_b - hi_a, lo_a - hi_b));
 }
 
-// One queued voter (48 B, read by the whole warp as three broadcast LDS.128).  The two
-// receivers of a lane share x and y, so the x/y terms of every dot product are scalar
-// and only the z terms are packed pairs; the pairs are stored duplicated so that they
-// come out of the load as aligned register pairs.
-struct __align__(16) QEntry {
-  float4 a;  // {-x, -y, nx, ny}
-  float4 b;  // {nx/2, ny/2, nz, nz/2}
-  float4 c;  // {-z, -z, lw, lw}   lw: see TV_SQRTW below
-};
-
-constexpr int TV_QCAP = 64;    // ring capacity per class (entries); drained 32 at a time
-constexpr int TV_DRAIN = 32;
-constexpr float TV_R2_EPS = 1e-30f;  // keeps 1/r^2 finite for the self vote (r = 0, d.n = 0)
+constexpr int TV_DRAIN = 32;             // voters evaluated per drain
+constexpr int TV_QCAP = 3 * TV_DRAIN;    // ring capacity (see the invariant in the kernel)
+constexpr float TV_R2_EPS = 1e-30f;      // keeps 1/r^2 finite for the self vote (r = 0, d.n = 0)
 
 __device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }  // FFMA2 takes scalar (.F32) operands
 
@@ -341,34 +351,35 @@ __device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }  // 
 // With r = receiver - voter, r2 = |r|^2, d = r.n, q = d/r2:  sin^2 = q*d (cos^2 = 1 - q*d),
 // rotated normal v = n - 2 q r (feature.hpp:2341-2351; its sign does not matter for
 // v v^T, so surfaces and curves share it).  We accumulate with h = v/2 = n/2 - q r and
-// fold the factor 4 into the weight.
+// fold the factor 4 into the weight.  The two receivers share x and y, so the x/y terms
+// of r2 and d are scalar; everything else is packed FP32 (FFMA2/FMUL2, whose scalar
+// operand form reads a shared value without a register pair).
 //   SQRTW (exponent 4, all weights > 0): weight*decay*ang^2*4 = (sE*ang)^2 with
-//     sE = exp2(r2*neg_c/2 + lw), lw = log2(4*weight)/2; T += (sE*ang*h)(sE*ang*h)^T
+//     sE = exp2(r2*neg_c/2 + log2(4w)/2);  T += (sE*ang*h)(sE*ang*h)^T
 //   otherwise: w = decay*ang^(e/2)*weight*4,  T += (w h) h^T
-// BOUNDARY: the voter's support sphere cuts through the warp's patch: pairs outside the
-// support get weight 0.  Lattice points exactly on the shell r2 == hw^2 are kept or
-// dropped by float rounding in the reference's table (filter3d.hpp:546-601); the host
-// evaluates that table: all kept (every parameter set we have seen) or all dropped is
-// folded into lim_in = hw^2 +- 0.5; a mixed shell runs the SHELL kernels, which look
-// each on-shell pair up in the list of kept points.
-template <int EXPO, bool CURVES, bool POSW, bool BOUNDARY, bool SHELL>
-__device__ __forceinline__ void vote(const QEntry *q, float fx, float fy, float2 fz,
-                                     const GatherArgs &g, float2 negc, float2 T[6]) {
+// Pairs outside the support get weight 0.  Lattice points exactly on the shell
+// r2 == hw^2 are kept or dropped by float rounding in the reference's table
+// (filter3d.hpp:546-601); the host evaluates that table: all kept (every parameter set we
+// have seen) or all dropped is folded into lim_in = hw^2 +- 0.5; a mixed shell runs the
+// SHELL kernels, which look each on-shell pair up in the list of kept points.
+template <int EXPO, bool CURVES, bool POSW, bool SHELL>
+__device__ __forceinline__ void vote(const VoterRec *q, float fx, float fy, float2 fz,
+                                     const GatherArgs &g, float negc, float lim_in, float2 T[6]) {
   constexpr bool SQRTW = (EXPO == 4) && POSW;
   const float4 ea = q->a, eb = q->b, ec = q->c;
   const float rx = fx + ea.x, ry = fy + ea.y;
   const float rxy2 = fmaf(ry, ry, fmaf(rx, rx, TV_R2_EPS));
-  const float dxy = fmaf(ry, ea.w, rx * ea.z);
-  const float2 rz = __fadd2_rn(fz, make_float2(ec.x, ec.y));
+  const float dxy = fmaf(ry, eb.y, rx * eb.x);
+  const float2 rz = __fadd2_rn(fz, bc(ea.z));
   const float2 r2 = __ffma2_rn(rz, rz, bc(rxy2));
   const float2 d = __ffma2_rn(rz, bc(eb.z), bc(dxy));
   float2 ee;
   if (POSW) {
-    const float2 arg = __ffma2_rn(r2, negc, make_float2(ec.z, ec.w));
+    const float2 arg = __ffma2_rn(r2, bc(negc), bc(SQRTW ? ea.w : eb.w));
     ee = make_float2(fast_ex2(arg.x), fast_ex2(arg.y));
   } else {
-    const float2 arg = __fmul2_rn(r2, negc);
-    ee = __fmul2_rn(make_float2(fast_ex2(arg.x), fast_ex2(arg.y)), make_float2(ec.z, ec.w));
+    const float2 arg = __fmul2_rn(r2, bc(negc));
+    ee = __fmul2_rn(make_float2(fast_ex2(arg.x), fast_ex2(arg.y)), bc(ec.w));
   }
   const float2 ninv = make_float2(fast_rcp(-r2.x), fast_rcp(-r2.y));
   const float2 qn = __fmul2_rn(d, ninv);  // -q
@@ -387,49 +398,49 @@ __device__ __forceinline__ void vote(const QEntry *q, float fx, float fy, float2
                            fast_ex2(g.half_exp * fast_lg2(fmaxf(ang2.y, 0.0f))));
     w = __fmul2_rn(ee, ang);
   }
-  if (BOUNDARY) {
+  {
     const float2 wfull = w;
-    w.x = (r2.x < g.lim_in) ? w.x : 0.0f;
-    w.y = (r2.y < g.lim_in) ? w.y : 0.0f;
+    w.x = (r2.x < lim_in) ? w.x : 0.0f;
+    w.y = (r2.y < lim_in) ? w.y : 0.0f;
     if (SHELL) {
-      const bool sx = r2.x >= g.lim_in && r2.x < g.lim_pass, sy = r2.y >= g.lim_in && r2.y < g.lim_pass;
+      const bool sx = r2.x >= lim_in && r2.x < g.lim_pass, sy = r2.y >= lim_in && r2.y < g.lim_pass;
       if (__any_sync(0xffffffffu, sx || sy)) {
         if (sx) w.x = wfull.x * shell_weight(g.shell, g.n_shell, rx, ry, rz.x);
         if (sy) w.y = wfull.y * shell_weight(g.shell, g.n_shell, rx, ry, rz.y);
       }
     }
   }
-  const float2 hx = __ffma2_rn(qn, bc(rx), bc(eb.x));
-  const float2 hy = __ffma2_rn(qn, bc(ry), bc(eb.y));
-  const float2 hz = __ffma2_rn(qn, rz, bc(eb.w));
+  const float2 hx = __ffma2_rn(qn, bc(rx), bc(ec.x));
+  const float2 hy = __ffma2_rn(qn, bc(ry), bc(ec.y));
+  const float2 hz = __ffma2_rn(qn, rz, bc(ec.z));
   const float2 wx = __fmul2_rn(w, hx), wy = __fmul2_rn(w, hy), wz = __fmul2_rn(w, hz);
+  // (ordered so that consecutive FFMA2 share their first operand: operand-reuse cache)
   if (SQRTW) {
     T[0] = __ffma2_rn(wx, wx, T[0]);
-    T[1] = __ffma2_rn(wy, wy, T[1]);
-    T[2] = __ffma2_rn(wz, wz, T[2]);
     T[3] = __ffma2_rn(wx, wy, T[3]);
-    T[4] = __ffma2_rn(wy, wz, T[4]);
     T[5] = __ffma2_rn(wx, wz, T[5]);
+    T[1] = __ffma2_rn(wy, wy, T[1]);
+    T[4] = __ffma2_rn(wy, wz, T[4]);
+    T[2] = __ffma2_rn(wz, wz, T[2]);
   } else {
     T[0] = __ffma2_rn(wx, hx, T[0]);
-    T[1] = __ffma2_rn(wy, hy, T[1]);
-    T[2] = __ffma2_rn(wz, hz, T[2]);
     T[3] = __ffma2_rn(wx, hy, T[3]);
-    T[4] = __ffma2_rn(wy, hz, T[4]);
     T[5] = __ffma2_rn(wx, hz, T[5]);
+    T[1] = __ffma2_rn(wy, hy, T[1]);
+    T[4] = __ffma2_rn(wy, hz, T[4]);
+    T[2] = __ffma2_rn(wz, hz, T[2]);
   }
 }
 
-// n consecutive entries (n even).  A ring's head is always 0 or TV_DRAIN and at most
-// TV_DRAIN entries are drained at a time, so a drain never wraps.
-template <int EXPO, bool CURVES, bool POSW, bool BOUNDARY, bool SHELL>
-__device__ __forceinline__ void drain(const QEntry *q, int n, float fx, float fy, float2 fz,
-                                      const GatherArgs &g, float2 negc, float2 T[6]) {
-  const QEntry *end = q + n;
+// n consecutive ring entries (n even; a drain never wraps, see the kernel)
+template <int EXPO, bool CURVES, bool POSW, bool SHELL>
+__device__ __forceinline__ void drain(const VoterRec *q, int n, float fx, float fy, float2 fz,
+                                      const GatherArgs &g, float negc, float lim_in, float2 T[6]) {
+  const VoterRec *end = q + n;
 #pragma unroll 1
   for (; q != end; q += 2) {
-    vote<EXPO, CURVES, POSW, BOUNDARY, SHELL>(q, fx, fy, fz, g, negc, T);
-    vote<EXPO, CURVES, POSW, BOUNDARY, SHELL>(q + 1, fx, fy, fz, g, negc, T);
+    vote<EXPO, CURVES, POSW, SHELL>(q, fx, fy, fz, g, negc, lim_in, T);
+    vote<EXPO, CURVES, POSW, SHELL>(q + 1, fx, fy, fz, g, negc, lim_in, T);
   }
 }
 
@@ -438,21 +449,25 @@ __device__ __forceinline__ void drain(const QEntry *q, int n, float fx, float fy
 // tile but never synchronise with each other.  A warp
 //   1. builds the table of brick rows (contiguous ranges of the brick-ordered voter
 //      list) whose bricks can reach its patch,
-//   2. streams them 32 candidates at a time -- one candidate per lane, loaded straight
-//      from L1/L2 one batch ahead -- and classifies each against the patch: out of
-//      reach / INNER (all 64 receivers strictly inside the support sphere) / BOUNDARY,
-//   3. appends the survivors to two warp-private shared-memory rings and, whenever a ring
-//      holds 32, drains them: every lane evaluates the voter (broadcast LDS) on its two
-//      receivers.  INNER votes need no support test at all.
+//   2. streams them 32 candidates at a time: each lane loads the position of one
+//      candidate (one batch ahead, straight from L1/L2), tests the exact distance between
+//      the voter and the patch box against the support radius, and -- if the voter can
+//      reach the patch -- copies its 48-byte record with cp.async into the next free slot
+//      of a warp-private shared-memory ring (slot = ballot rank),
+//   3. whenever the ring held >= 32 voters BEFORE the current batch was appended, waits
+//      for all but the newest cp.async group and drains 32 voters: every lane evaluates
+//      the voter (three broadcast LDS.128) on its two receivers.
+// Ring invariant: capacity 96, head in {0, 32, 64}; before a batch count <= 63, the
+// batch adds <= 32 (95 < 96 entries live), and a drain removes the 32 oldest, all of
+// which belong to cp.async groups older than the newest one.
 template <int EXPO, bool CURVES, bool POSW, bool SHELL>
 __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(GatherArgs g) {
   extern __shared__ __align__(16) unsigned char tv_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t per_warp = 2 * TV_QCAP * sizeof(QEntry) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t);
+  const size_t per_warp = TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t);
   unsigned char *mine = tv_smem + warp * ((per_warp + 15) & ~(size_t)15);
-  QEntry *ring_i = reinterpret_cast<QEntry *>(mine);
-  QEntry *ring_b = ring_i + TV_QCAP;
-  uint32_t *row_start = reinterpret_cast<uint32_t *>(ring_b + TV_QCAP);
+  VoterRec *ring = reinterpret_cast<VoterRec *>(mine);
+  uint32_t *row_start = reinterpret_cast<uint32_t *>(ring + TV_QCAP);
   uint32_t *row_pref = row_start + g.row_cap;  // [row_cap + 1]
 
   const int tile = blockIdx.x;
@@ -508,76 +523,77 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
   const float2 fz = make_float2((float)iz, (float)(iz + 1));
   const float pcx = px + 1.5f, pcy = py + 1.5f, pcz = pz + 1.5f;
   constexpr bool SQRTW = (EXPO == 4) && POSW;
-  const float nc = SQRTW ? 0.5f * g.neg_c : g.neg_c;
-  const float2 negc = make_float2(nc, nc);
+  const float negc = SQRTW ? 0.5f * g.neg_c : g.neg_c;
+  const float lim_in = g.lim_in, lim_pass = g.lim_pass;
   float2 T[6];
 #pragma unroll
   for (int k = 0; k < 6; k++) T[k] = make_float2(0.0f, 0.0f);
 
-  // ---- 2./3. stream, classify, vote -----------------------------------------------------
+  // ---- 2./3. stream, cull, vote ---------------------------------------------------------
   int cur_row = 0;  // per-lane cursor into the row table (flat indices only grow)
-  auto fetch = [&](uint32_t e, float4 &a, float4 &b) {
-    if (e < total) {
-      while (e >= row_pref[cur_row + 1]) cur_row++;
-      const uint32_t gi = row_start[cur_row] + (e - row_pref[cur_row]);
-      a = __ldg(g.va + gi);
-      b = __ldg(g.vb + gi);
-    }
+  auto locate = [&](uint32_t e) -> const VoterRec * {
+    while (e >= row_pref[cur_row + 1]) cur_row++;
+    return g.rec + (row_start[cur_row] + (e - row_pref[cur_row]));
   };
-  auto put = [&](QEntry *slot, const float4 &a, const float4 &n) {
-    float lw;
-    if (SQRTW) lw = fmaf(0.5f, fast_lg2(a.w), 1.0f);      // log2(4 w)/2
-    else if (POSW) lw = fast_lg2(a.w) + 2.0f;             // log2(4 w)
-    else lw = 4.0f * a.w;
-    slot->a = make_float4(-a.x, -a.y, n.x, n.y);
-    slot->b = make_float4(0.5f * n.x, 0.5f * n.y, n.z, 0.5f * n.z);
-    slot->c = make_float4(-a.z, -a.z, lw, lw);
-  };
-  int head_i = 0, cnt_i = 0, head_b = 0, cnt_b = 0;
-  float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
-  fetch(lane, na, nb);
-  for (uint32_t base = 0; base < total; base += 32) {
-    const float4 a = na, b = nb;
-    const bool valid = base + lane < total;
-    fetch(base + 32 + lane, na, nb);
-    const float ax = fabsf(a.x - pcx), ay = fabsf(a.y - pcy), az = fabsf(a.z - pcz);
-    const float gx = fmaxf(ax - 1.5f, 0.0f), gy = fmaxf(ay - 1.5f, 0.0f), gz = fmaxf(az - 1.5f, 0.0f);
-    const float hx = ax + 1.5f, hy = ay + 1.5f, hz = az + 1.5f;
-    const float dmin2 = fmaf(gx, gx, fmaf(gy, gy, gz * gz));
-    const float dmax2 = fmaf(hx, hx, fmaf(hy, hy, hz * hz));
-    const bool pass = valid && dmin2 < g.lim_pass;
-    const bool inner = pass && dmax2 < g.lim_in;
-    const unsigned mi = __ballot_sync(0xffffffffu, inner);
-    const unsigned mb = __ballot_sync(0xffffffffu, pass && !inner);
-    const unsigned below = (1u << lane) - 1u;
-    if (inner) put(ring_i + ((head_i + cnt_i + __popc(mi & below)) & (TV_QCAP - 1)), a, b);
-    else if (pass) put(ring_b + ((head_b + cnt_b + __popc(mb & below)) & (TV_QCAP - 1)), a, b);
-    cnt_i += __popc(mi);
-    cnt_b += __popc(mb);
-    __syncwarp();
-    if (cnt_i >= TV_DRAIN) {
-      drain<EXPO, CURVES, POSW, false, false>(ring_i + head_i, TV_DRAIN, fx, fy, fz, g, negc, T);
-      head_i = (head_i + TV_DRAIN) & (TV_QCAP - 1);
-      cnt_i -= TV_DRAIN;
-    }
-    if (cnt_b >= TV_DRAIN) {
-      drain<EXPO, CURVES, POSW, true, SHELL>(ring_b + head_b, TV_DRAIN, fx, fy, fz, g, negc, T);
-      head_b = (head_b + TV_DRAIN) & (TV_QCAP - 1);
-      cnt_b -= TV_DRAIN;
-    }
-    __syncwarp();
+  const float4 nowhere = make_float4(-1.0e9f, -1.0e9f, -1.0e9f, 0.0f);
+  int head = 0, cnt = 0;
+  const VoterRec *nrec = g.rec;
+  float4 na = nowhere;
+  if (lane < total) {
+    nrec = locate(lane);
+    na = __ldg(&nrec->a);
   }
-  // leftovers, padded to an even count with a zero-weight voter
-  {
-    const float4 far = make_float4(-1.0e4f, -1.0e4f, -1.0e4f, 0.0f);  // lg2(0) = -inf, ex2(-inf) = 0
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane == 0) {
-      if (cnt_i & 1) put(ring_i + ((head_i + cnt_i) & (TV_QCAP - 1)), far, zero);
-      if (cnt_b & 1) put(ring_b + ((head_b + cnt_b) & (TV_QCAP - 1)), far, zero);
+  for (uint32_t base = 0; base < total; base += 32) {
+    const float4 a = na;
+    const VoterRec *rec = nrec;
+    na = nowhere;
+    if (base + 32 + lane < total) {
+      nrec = locate(base + 32 + lane);
+      na = __ldg(&nrec->a);
     }
-    __syncwarp();
-    drain<EXPO, CURVES, POSW, false, false>(ring_i + head_i, (cnt_i + 1) & ~1, fx, fy, fz, g, negc, T);
-    drain<EXPO, CURVES, POSW, true, SHELL>(ring_b + head_b, (cnt_b + 1) & ~1, fx, fy, fz, g, negc, T);
+    // exact distance from the voter (a holds the NEGATED position) to the patch box
+    const float gx = fmaxf(fabsf(a.x + pcx) - 1.5f, 0.0f);
+    const float gy = fmaxf(fabsf(a.y + pcy) - 1.5f, 0.0f);
+    const float gz = fmaxf(fabsf(a.z + pcz) - 1.5f, 0.0f);
+    const bool pass = fmaf(gx, gx, fmaf(gy, gy, gz * gz)) < lim_pass;
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    const int before = cnt;
+    if (pass) {
+      int slot = head + cnt + __popc(m & ((1u << lane) - 1u));
+      if (slot >= TV_QCAP) slot -= TV_QCAP;
+      VoterRec *dst = ring + slot;
+      cp_async16(&dst->a, &rec->a);
+      cp_async16(&dst->b, &rec->b);
+      cp_async16(&dst->c, &rec->c);
+    }
+    cp_async_commit();
+    cnt += __popc(m);
+    if (before >= TV_DRAIN) {
+      cp_async_wait<1>();
+      __syncwarp();
+      drain<EXPO, CURVES, POSW, SHELL>(ring + head, TV_DRAIN, fx, fy, fz, g, negc, lim_in, T);
+      head = (head + TV_DRAIN == TV_QCAP) ? 0 : head + TV_DRAIN;
+      cnt -= TV_DRAIN;
+      __syncwarp();
+    }
+  }
+  // leftovers (<= 95), padded to an even count with a zero-weight voter
+  cp_async_wait<0>();
+  if (lane == 0 && (cnt & 1)) {
+    int slot = head + cnt;
+    if (slot >= TV_QCAP) slot -= TV_QCAP;
+    const float ninf = __int_as_float(0xff800000u);  // ex2(-inf) = 0
+    ring[slot].a = make_float4(1.0e4f, 1.0e4f, 1.0e4f, ninf);
+    ring[slot].b = make_float4(0.f, 0.f, 0.f, ninf);
+    ring[slot].c = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  cnt = (cnt + 1) & ~1;
+  while (cnt > 0) {
+    const int n = min(cnt, min(TV_DRAIN, TV_QCAP - head));
+    drain<EXPO, CURVES, POSW, SHELL>(ring + head, n, fx, fy, fz, g, negc, lim_in, T);
+    head = (head + n == TV_QCAP) ? 0 : head + n;
+    cnt -= n;
   }
 
   // ---- epilogue ---------------------------------------------------------------------
@@ -639,7 +655,7 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   const i64 n_scan_blocks = (n_bricks + SCAN_B - 1) / SCAN_B;
   Scratch<uint32_t> sums(ctx, n_scan_blocks + 2);   // block sums, [n] = total, [n+1] = non-positive-weight flag
   uint32_t n_voters = 0, nonpos = 0;
-  Scratch<float4> va, vb;
+  Scratch<VoterRec> rec;
   {
     StageTimer t(ctx, "compact");
     voter_count_kernel<<<(unsigned)n_bricks, BR3, 0, ctx->stream>>>(vs, counts.get());
@@ -655,13 +671,12 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
     VCK(cudaMemcpyAsync(&n_voters, sums.get() + n_scan_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     VCK(cudaStreamSynchronize(ctx->stream));
     // (a 32-bit voter count: 4.29e9 voters would need 137 GB of voter records anyway)
-    va.reset(ctx, std::max<size_t>(n_voters, 1));
-    vb.reset(ctx, std::max<size_t>(n_voters, 1));
+    rec.reset(ctx, std::max<size_t>(n_voters, 1));
     if (n_voters > 0) {
       DirSrc ds{direction, smoothed, ridge_sigma, eival_order, z_offset, nz_global};
       VCK(cudaMemsetAsync(sums.get() + n_scan_blocks + 1, 0, sizeof(uint32_t), ctx->stream));
       voter_fill_kernel<<<(unsigned)n_bricks, BR3, 0, ctx->stream>>>(vs, ds, off.get(), 1.0f / info.total,
-                                                                     va.get(), vb.get(),
+                                                                     rec.get(),
                                                                      sums.get() + n_scan_blocks + 1);
       VCK(cudaGetLastError());
       ctx->count_launch();
@@ -678,7 +693,7 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
                         cudaMemcpyHostToDevice, ctx->stream));
 
   GatherArgs g;
-  g.va = va.get(); g.vb = vb.get(); g.off = off.get();
+  g.rec = rec.get(); g.off = off.get();
   g.shell = shell.get(); g.n_shell = (int)info.shell_keep.size();
   g.nx = (int)nx; g.ny = (int)ny; g.nz = nz_local;
   g.nbx = nbx; g.nby = nby; g.nbz = nbz;
@@ -703,7 +718,7 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
     const unsigned grid = (unsigned)n_tiles;
     // POSW: all voter weights > 0 (always true for the planar ridge score), so log2(weight)
     // rides in the decay exponent
-    const size_t per_warp = (2 * TV_QCAP * sizeof(QEntry) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t) + 15) & ~(size_t)15;
+    const size_t per_warp = (TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t) + 15) & ~(size_t)15;
     const size_t smem = (TV_THREADS / 32) * per_warp;
 #define TV_LAUNCH1(E, C, P, S)                                                                            \
     do {                                                                                                  \
