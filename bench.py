@@ -251,6 +251,7 @@ def main():
         o0, o1 = pipe.plan.own_local
         pairs = ctx.tv_count_pairs(pipe.saliency[v0:v1], pipe.threshold, 20, recv=(o0 - v0, o1 - v0))
     fp32_peak = ctx.fp32_peak(300.0)
+    fp32_peak_3op = ctx.fp32_peak(300.0, three_operand=True)
     tv_ms = stage["tv"]
     achieved = 35.0 * pairs / (tv_ms * 1e-3) / 1e12
     roofline = {"kernel": "tv_gather_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
@@ -258,6 +259,7 @@ def main():
                 "traffic": NCU_TRAFFIC_BYTES.get(name) if world == 1 else None,
                 "peak_source": "measured in this run: register-resident FFMA chains (visfd_cuda_fp32_peak); "
                                "MEASURED_PEAKS.json holds HBM and bf16 tensor peaks only",
+                "peak_3_register_operands": fp32_peak_3op, "frac_of_3_operand_peak": achieved / fp32_peak_3op,
                 "algorithmic_flop": 35.0 * pairs, "pairs": int(pairs), "voters": int(n_voters),
                 "kernel_ms": tv_ms, "share_of_step": tv_ms / ms_step}
 

@@ -254,6 +254,9 @@ int visfd_cuda_tv_count_pairs(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz
 int visfd_cuda_fp32_peak(visfd_ctx *ctx, double ms, double *tflops);
 /* The same with packed FFMA2 (fma.rn.f32x2) chains. */
 int visfd_cuda_fp32_peak_packed(visfd_ctx *ctx, double ms, double *tflops);
+/* FFMA with three distinct register operands (acc += x*y): register-file bandwidth (two
+ * 32-bit operands per lane per clock) holds this form to ~2/3 of the chain peak. */
+int visfd_cuda_fp32_peak_3op(visfd_ctx *ctx, double ms, double *tflops);
 
 /* ---- threshold / mask maps -------------------------------------------------------- */
 #define VISFD_THRESH_SINGLE 1 /* in > a ? outB : outA           handlers.cpp:1049-1053 */

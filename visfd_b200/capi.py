@@ -187,9 +187,11 @@ class Context:
     def last_voter_count(self):
         return self.lib.visfd_cuda_last_voter_count(self.h)
 
-    def fp32_peak(self, ms=200.0, packed=False):
+    def fp32_peak(self, ms=200.0, packed=False, three_operand=False):
         t = _d()
         fn = self.lib.visfd_cuda_fp32_peak_packed if packed else self.lib.visfd_cuda_fp32_peak
+        if three_operand:
+            fn = self.lib.visfd_cuda_fp32_peak_3op
         self._ck(fn(self.h, _d(ms), C.byref(t)))
         return t.value
 

@@ -427,14 +427,21 @@ int visfd_cuda_tv_count_pairs(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz
 int visfd_cuda_fp32_peak(visfd_ctx *ctx, double ms, double *tflops) {
   API_BEGIN(ctx)
   VREQUIRE(tflops, "NULL argument");
-  *tflops = fp32_peak_device(ctx, ms, false);
+  *tflops = fp32_peak_device(ctx, ms, 0);
   API_END(ctx)
 }
 
 int visfd_cuda_fp32_peak_packed(visfd_ctx *ctx, double ms, double *tflops) {
   API_BEGIN(ctx)
   VREQUIRE(tflops, "NULL argument");
-  *tflops = fp32_peak_device(ctx, ms, true);
+  *tflops = fp32_peak_device(ctx, ms, 1);
+  API_END(ctx)
+}
+
+int visfd_cuda_fp32_peak_3op(visfd_ctx *ctx, double ms, double *tflops) {
+  API_BEGIN(ctx)
+  VREQUIRE(tflops, "NULL argument");
+  *tflops = fp32_peak_device(ctx, ms, 2);
   API_END(ctx)
 }
 

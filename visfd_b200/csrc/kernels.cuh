@@ -92,6 +92,6 @@ void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *src, c
 // ---- util.cu ----------------------------------------------------------------------
 i64 tv_count_pairs_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *sal, float thr,
                           const float *mask_src, const float *mask_dst, int hw, int recv_z0, int recv_z1);
-double fp32_peak_device(visfd_ctx *ctx, double ms_target, bool packed);
+double fp32_peak_device(visfd_ctx *ctx, double ms_target, int mode);  // 0 FFMA chains, 1 packed FFMA2, 2 three register operands
 
 }  // namespace visfd_cuda

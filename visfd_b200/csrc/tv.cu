@@ -297,7 +297,7 @@ struct GatherArgs {
   float hw2;              // (float) hw*hw
   float lim_in;           // pairs with r2 < lim_in get the full weight ...
   float lim_pass;         // ... pairs with r2 in [lim_in, lim_pass) sit on the shell (SHELL kernels only)
-  float neg_c;            // -log2(e)/sigma^2
+  float neg_c;            // -log2(e)/sigma^2 (half of it for the SQRTW kernels)
   float half_exp;         // exponent/2, generic path
   const float *mask_dst;  // slab-indexed, or NULL
   float *tensor;          // own-planes-indexed * 6, or NULL
@@ -522,8 +522,7 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
   const float fx = (float)ix, fy = (float)iy;
   const float2 fz = make_float2((float)iz, (float)(iz + 1));
   const float pcx = px + 1.5f, pcy = py + 1.5f, pcz = pz + 1.5f;
-  constexpr bool SQRTW = (EXPO == 4) && POSW;
-  const float negc = SQRTW ? 0.5f * g.neg_c : g.neg_c;
+  const float negc = g.neg_c;  // already halved on the host for the SQRTW kernels
   const float lim_in = g.lim_in, lim_pass = g.lim_pass;
   float2 T[6];
 #pragma unroll
@@ -730,7 +729,10 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
     do {                                                  \
       if (mixed_shell) TV_LAUNCH1(E, C, false, true);     \
       else if (nonpos) TV_LAUNCH1(E, C, false, false);    \
-      else TV_LAUNCH1(E, C, true, false);                 \
+      else {                                              \
+        if (E == 4) g.neg_c *= 0.5f;                      \
+        TV_LAUNCH1(E, C, true, false);                    \
+      }                                                   \
     } while (0)
     if (p.curves) {
       if (p.exponent == 2) TV_LAUNCH(2, true);
