@@ -102,6 +102,38 @@ __device__ __forceinline__ float tap_acc(float acc, float h, float v) {
   return __fadd_rn(acc, __fmul_rn(h, v));
 }
 
+// Packed FP32 (FMUL2 / FADD2 / FFMA2, each lane-wise IEEE round-to-nearest like the scalar
+// forms, so EXACT stays bit-exact): half the issue slots for the same arithmetic.
+// (ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- unlike the scalar .rn
+// forms, and whatever -fmad says -- so EXACT uses a packed product and two scalar sums:
+// three instructions per two taps instead of four.)
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+  return r;
+}
+__device__ __forceinline__ float2 bits_f2(unsigned long long b) {
+  float2 v;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(b));
+  return v;
+}
+__device__ __forceinline__ float2 mul_then_add2(float2 acc, float2 a, float2 b) {
+  unsigned long long p;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  const float2 pr = bits_f2(p);
+  return make_float2(__fadd_rn(acc.x, pr.x), __fadd_rn(acc.y, pr.y));
+}
+template <int MODE>
+__device__ __forceinline__ float2 tap_acc2(float2 acc, float h, float2 v) {
+  if (MODE == MODE_FAST) return __ffma2_rn(v, make_float2(h, h), acc);
+  return mul_then_add2(acc, make_float2(h, h), v);
+}
+template <int MODE>
+__device__ __forceinline__ float2 tap_acc2(float2 acc, float2 h, float v) {
+  if (MODE == MODE_FAST) return __ffma2_rn(h, make_float2(v, v), acc);
+  return mul_then_add2(acc, h, make_float2(v, v));
+}
+
 // in/out: volumes; the sweep axis has n_axis entries with stride s_axis (floats);
 // the third ("other") dimension has stride s_other and is indexed by blockIdx.z.
 // mask (optional): FAST: multiplied into the input while staging; EXACT_MASKED: staged
@@ -201,6 +233,204 @@ sweep_axis_kernel(const float *__restrict__ in, float *__restrict__ out,
       if (xl + 1 < nx) p[1] = acc[r].y;
       if (xl + 2 < nx) p[2] = acc[r].z;
       if (xl + 3 < nx) p[3] = acc[r].w;
+    }
+  }
+}
+
+// ---- un-masked Y / Z sweep, tap-stationary --------------------------------------------
+// CTA = 8 warps x 32 lanes: 128 columns (float4 per lane) x 32 outputs along the axis,
+// warp w owns outputs 4w..4w+3.  The CTA stages the ntap8 + 31 input rows it needs once
+// (ntap8 = taps rounded up to a multiple of 8, zero taps at the end).  A thread keeps a
+// window of 8 input rows in registers, indexed by k mod 8 where row k is input position
+// a0 + hw - k: output r takes tap t from row k = t - r, so one group of 4 taps needs
+// rows 4g-3 .. 4g+3 -- 4 new rows per group, 16 useful mul+add per float4 column, and all
+// register indices static after unrolling two groups.  Taps are visited in ascending order
+// for every output: the reference's accumulation order (filter1d.hpp:96-101).
+constexpr int A2_S = 32;   // outputs along the axis per CTA
+constexpr int A2_R = 4;    // outputs per thread
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 4)
+sweep_axis2_kernel(const float *__restrict__ in, float *__restrict__ out,
+                   const float *__restrict__ taps, int hw, int ntap8, int nx, i64 n_axis,
+                   i64 s_axis, i64 s_other, int vec_ok) {
+  extern __shared__ __align__(16) float smem[];
+  const int rows = ntap8 + A2_S - 1;
+  float *tile = smem;                          // [rows][AX_TX]
+  float *tp = smem + (size_t)rows * AX_TX;     // [ntap8]
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  const int tid = wy * 32 + lane;
+  const int x0 = blockIdx.x * AX_TX;
+  const i64 A0 = (i64)blockIdx.y * A2_S;
+  const i64 base = (i64)blockIdx.z * s_other;
+  const int ntap = 2 * hw + 1;
+  for (int k = tid; k < ntap8; k += 256) tp[k] = (k < ntap) ? taps[k] : 0.0f;
+  // tile row rho holds input position lo + rho
+  const i64 lo = A0 + hw - ntap8 + 1;
+  const int xl = x0 + 4 * lane;
+  for (int r = wy; r < rows; r += 8) {
+    const i64 a = lo + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a >= 0 && a < n_axis) {
+      const float *p = in + base + a * s_axis + xl;
+      if (vec_ok && xl + 3 < nx) {
+        v = ld4(p);
+      } else {
+        if (xl + 0 < nx) v.x = __ldg(p + 0);
+        if (xl + 1 < nx) v.y = __ldg(p + 1);
+        if (xl + 2 < nx) v.z = __ldg(p + 2);
+        if (xl + 3 < nx) v.w = __ldg(p + 3);
+      }
+    }
+    *reinterpret_cast<float4 *>(tile + (size_t)r * AX_TX + 4 * lane) = v;
+  }
+  __syncthreads();
+
+  float4 acc[A2_R];
+#pragma unroll
+  for (int r = 0; r < A2_R; r++) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // row k of this warp = tile row A2_R*wy + ntap8 - 1 - k
+  const float *row0 = tile + (size_t)(A2_R * wy + ntap8 - 1) * AX_TX + 4 * lane;
+#define ROW(k) (*reinterpret_cast<const float4 *>(row0 - (ptrdiff_t)(k) * AX_TX))
+  float4 win[8];
+  win[5] = ROW(-3);
+  win[6] = ROW(-2);
+  win[7] = ROW(-1);
+#define TAP4(h, tt, base_idx)                                                     \
+  _Pragma("unroll") for (int r = 0; r < A2_R; r++) {                              \
+    const float4 v = win[((base_idx) + (tt) - r) & 7];                            \
+    acc[r].x = tap_acc<MODE>(acc[r].x, h, v.x);                                   \
+    acc[r].y = tap_acc<MODE>(acc[r].y, h, v.y);                                   \
+    acc[r].z = tap_acc<MODE>(acc[r].z, h, v.z);                                   \
+    acc[r].w = tap_acc<MODE>(acc[r].w, h, v.w);                                   \
+  }
+  for (int k0 = 0; k0 < ntap8; k0 += 8) {
+    const float4 ha = *reinterpret_cast<const float4 *>(tp + k0);
+    const float4 hb = *reinterpret_cast<const float4 *>(tp + k0 + 4);
+    win[0] = ROW(k0 + 0);
+    win[1] = ROW(k0 + 1);
+    win[2] = ROW(k0 + 2);
+    win[3] = ROW(k0 + 3);
+    TAP4(ha.x, 0, 0) TAP4(ha.y, 1, 0) TAP4(ha.z, 2, 0) TAP4(ha.w, 3, 0)
+    win[4] = ROW(k0 + 4);
+    win[5] = ROW(k0 + 5);
+    win[6] = ROW(k0 + 6);
+    win[7] = ROW(k0 + 7);
+    TAP4(hb.x, 0, 4) TAP4(hb.y, 1, 4) TAP4(hb.z, 2, 4) TAP4(hb.w, 3, 4)
+  }
+#undef TAP4
+#undef ROW
+#pragma unroll
+  for (int r = 0; r < A2_R; r++) {
+    const i64 a = A0 + A2_R * wy + r;
+    if (a >= n_axis) break;
+    float *p = out + base + a * s_axis + xl;
+    if (vec_ok && xl + 3 < nx) {
+      *reinterpret_cast<float4 *>(p) = acc[r];
+    } else {
+      if (xl + 0 < nx) p[0] = acc[r].x;
+      if (xl + 1 < nx) p[1] = acc[r].y;
+      if (xl + 2 < nx) p[2] = acc[r].z;
+      if (xl + 3 < nx) p[3] = acc[r].w;
+    }
+  }
+}
+
+// ---- the same with the loads pipelined (cp.async) ------------------------------------------
+// One CTA covers A3_NCH chunks of 32 outputs along the axis.  All rows of the tile are
+// requested up front with cp.async (LDGSTS, zero-fill outside the volume), one commit
+// group per chunk, so a CTA has its whole tile (tens of KB) in flight while it computes
+// the chunks that have already landed; with 3 CTAs per SM that is > 100 KB of loads in
+// flight per SM, enough to cover the DRAM latency at full bandwidth.  Needs float4-aligned
+// rows (nx % 4 == 0); sweep_axis2_kernel handles the ragged case.
+constexpr int A3_NCH = 3;
+
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, bool valid) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 3)
+sweep_axis3_kernel(const float *__restrict__ in, float *__restrict__ out,
+                   const float *__restrict__ taps, int hw, int ntap8, int nx, i64 n_axis,
+                   i64 s_axis, i64 s_other) {
+  extern __shared__ __align__(16) float smem[];
+  const int rows = ntap8 - 1 + A3_NCH * A2_S;
+  float *tile = smem;                          // [rows][AX_TX]
+  float *tp = smem + (size_t)rows * AX_TX;     // [ntap8]
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  const int tid = wy * 32 + lane;
+  const int xl = blockIdx.x * AX_TX + 4 * lane;
+  const i64 A0 = (i64)blockIdx.y * (A3_NCH * A2_S);
+  const i64 base = (i64)blockIdx.z * s_other;
+  const i64 lo = A0 + hw - ntap8 + 1;          // tile row rho holds input position lo + rho
+  const bool xin = xl < nx;
+#pragma unroll
+  for (int c = 0; c < A3_NCH; c++) {
+    const int r_begin = c == 0 ? 0 : ntap8 - 1 + A2_S * c, r_end = ntap8 - 1 + A2_S * (c + 1);
+    if (A0 + A2_S * c < n_axis) {
+      for (int r = r_begin + wy; r < r_end; r += 8) {
+        const i64 a = lo + r;
+        const bool ok = xin && a >= 0 && a < n_axis;
+        cp_async16_zfill(tile + (size_t)r * AX_TX + 4 * lane, ok ? in + base + a * s_axis + xl : in, ok);
+      }
+    }
+    cp_async_commit_group();
+  }
+  const int ntap = 2 * hw + 1;
+  for (int k = tid; k < ntap8; k += 256) tp[k] = (k < ntap) ? taps[k] : 0.0f;
+
+#pragma unroll 1
+  for (int c = 0; c < A3_NCH; c++) {
+    if (A0 + A2_S * c >= n_axis) break;   // uniform
+    if (c == 0) cp_async_wait_group<A3_NCH - 1>();
+    else if (c == 1) cp_async_wait_group<A3_NCH - 2>();
+    else cp_async_wait_group<0>();
+    __syncthreads();
+    float2 acc[A2_R][2];
+#pragma unroll
+    for (int r = 0; r < A2_R; r++) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
+    const float *row0 = tile + (size_t)(A2_S * c + A2_R * wy + ntap8 - 1) * AX_TX + 4 * lane;
+#define ROW(k) (*reinterpret_cast<const float4 *>(row0 - (ptrdiff_t)(k) * AX_TX))
+    float4 win[8];
+    win[5] = ROW(-3);
+    win[6] = ROW(-2);
+    win[7] = ROW(-1);
+#define TAP4(h, tt, base_idx)                                                     \
+  _Pragma("unroll") for (int r = 0; r < A2_R; r++) {                              \
+    const float4 v = win[((base_idx) + (tt) - r) & 7];                            \
+    acc[r][0] = tap_acc2<MODE>(acc[r][0], h, make_float2(v.x, v.y));              \
+    acc[r][1] = tap_acc2<MODE>(acc[r][1], h, make_float2(v.z, v.w));              \
+  }
+    for (int k0 = 0; k0 < ntap8; k0 += 8) {
+      const float4 ha = *reinterpret_cast<const float4 *>(tp + k0);
+      const float4 hb = *reinterpret_cast<const float4 *>(tp + k0 + 4);
+      win[0] = ROW(k0 + 0);
+      win[1] = ROW(k0 + 1);
+      win[2] = ROW(k0 + 2);
+      win[3] = ROW(k0 + 3);
+      TAP4(ha.x, 0, 0) TAP4(ha.y, 1, 0) TAP4(ha.z, 2, 0) TAP4(ha.w, 3, 0)
+      win[4] = ROW(k0 + 4);
+      win[5] = ROW(k0 + 5);
+      win[6] = ROW(k0 + 6);
+      win[7] = ROW(k0 + 7);
+      TAP4(hb.x, 0, 4) TAP4(hb.y, 1, 4) TAP4(hb.z, 2, 4) TAP4(hb.w, 3, 4)
+    }
+#undef TAP4
+#undef ROW
+    if (xin) {
+#pragma unroll
+      for (int r = 0; r < A2_R; r++) {
+        const i64 a = A0 + A2_S * c + A2_R * wy + r;
+        if (a < n_axis)
+          *reinterpret_cast<float4 *>(out + base + a * s_axis + xl) =
+              make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
+      }
     }
   }
 }
@@ -329,6 +559,141 @@ sweep_x_kernel(const float *__restrict__ in, float *__restrict__ out,
   }
 }
 
+// ---- X sweep with pipelined loads ---------------------------------------------------------
+// Same arithmetic as sweep_x_kernel; differences: the tile (64 rows in two chunks of 32)
+// is requested up front with cp.async and computed chunk by chunk; x tiles are the FASTEST
+// grid index, so the two CTAs that share a halo run back to back and the second finds it
+// in L2; the 7 taps of a step come from two aligned LDS.128; the epilogue does one
+// integer division per thread instead of two 64-bit ones per row.
+constexpr int X2_ROWS = 64;
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 3)
+sweep_x2_kernel(const float *__restrict__ in, float *__restrict__ out,
+                const float *__restrict__ taps, int hw, int nx, i64 nrows, int ny, int nxt,
+                XEpilogue ep) {
+  extern __shared__ __align__(16) float smem[];
+  const int hwpad = (hw + 3) & ~3;
+  const int pitch = XS_TX + 2 * hwpad + 4;
+  float *tile = smem;                        // [X2_ROWS][pitch]
+  float *tp = smem + (size_t)X2_ROWS * pitch;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
+  const int xt = blockIdx.x % nxt;
+  const i64 row0 = (i64)(blockIdx.x / nxt) * X2_ROWS;
+  const int x0 = xt * XS_TX;
+  const int nvec = (XS_TX + 2 * hwpad) >> 2;
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    if (row0 + 32 * c < nrows) {
+      for (int r = 32 * c + w; r < 32 * c + 32; r += 8) {
+        const i64 row = row0 + r;
+        const float *prow = in + row * (i64)nx;
+        for (int cc = lane; cc < nvec; cc += 32) {
+          const int x = x0 - hwpad + 4 * cc;
+          const bool ok = row < nrows && x >= 0 && x < nx;
+          cp_async16_zfill(tile + (size_t)r * pitch + 4 * cc, ok ? prow + x : in, ok);
+        }
+      }
+    }
+    cp_async_commit_group();
+  }
+  // taps, placed so that the 8-float window of every step is 16-byte aligned, plus a copy
+  // shifted by one float (tp1[k] = tp[k+1]) so that odd tap pairs are aligned pairs too
+  const int ntap = 2 * hw + 1;
+  const int P = 16 + ((3 - hw - hwpad) & 3);
+  const int tplen = (P + ntap + 16 + 3) & ~3;
+  float *tp1 = tp + tplen;
+  for (int k = tid; k < tplen; k += 256) {
+    const int t = k - P;
+    tp[k] = (t >= 0 && t < ntap) ? taps[t] : 0.0f;
+    tp1[k] = (t + 1 >= 0 && t + 1 < ntap) ? taps[t + 1] : 0.0f;
+  }
+  const int nsteps = (2 * hwpad + 4) >> 2;
+  const float *tb0 = tp + P + hw + hwpad - 3;
+  const float *tb1 = tp1 + P + hw + hwpad - 3;
+  const int xo = x0 + 4 * lane;
+  float dxv[4] = {1.f, 1.f, 1.f, 1.f};
+  if (ep.dx && xo < nx) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) dxv[e] = __ldg(ep.dx + xo + e);
+  }
+
+#pragma unroll 1
+  for (int c = 0; c < 2; c++) {
+    if (row0 + 32 * c >= nrows) break;  // uniform
+    if (c == 0) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
+    __syncthreads();
+    float2 acc[XS_RR][2];   // outputs (0,1) and (2,3) of each row
+#pragma unroll
+    for (int i = 0; i < XS_RR; i++) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+    const float *trow = tile + (size_t)(32 * c + w * XS_RR) * pitch + 4 * lane;
+    // highest input column first = the reference's accumulation order (tap index ascending)
+    for (int m = nsteps - 1; m >= 0; m--) {
+      // tap pairs (t[j], t[j+1]): even j from tp, odd j from the shifted copy
+      const float4 e0 = *reinterpret_cast<const float4 *>(tb0 - 4 * m);      // t0 t1 t2 t3
+      const float4 e1 = *reinterpret_cast<const float4 *>(tb0 - 4 * m + 4);  // t4 t5 t6 .
+      const float4 o0 = *reinterpret_cast<const float4 *>(tb1 - 4 * m);      // t1 t2 t3 t4
+      const float4 o1 = *reinterpret_cast<const float4 *>(tb1 - 4 * m + 4);  // t5 t6 . .
+      const float2 t01 = make_float2(e0.x, e0.y), t23 = make_float2(e0.z, e0.w), t45 = make_float2(e1.x, e1.y);
+      const float2 t12 = make_float2(o0.x, o0.y), t34 = make_float2(o0.z, o0.w), t56 = make_float2(o1.x, o1.y);
+#pragma unroll
+      for (int i = 0; i < XS_RR; i++) {
+        const float4 v = *reinterpret_cast<const float4 *>(trow + (size_t)i * pitch + 4 * m);
+        // output e takes tap t[e - c + 3] from input column c; c descending = taps ascending
+        acc[i][0] = tap_acc2<MODE>(acc[i][0], t01, v.w);
+        acc[i][1] = tap_acc2<MODE>(acc[i][1], t23, v.w);
+        acc[i][0] = tap_acc2<MODE>(acc[i][0], t12, v.z);
+        acc[i][1] = tap_acc2<MODE>(acc[i][1], t34, v.z);
+        acc[i][0] = tap_acc2<MODE>(acc[i][0], t23, v.y);
+        acc[i][1] = tap_acc2<MODE>(acc[i][1], t45, v.y);
+        acc[i][0] = tap_acc2<MODE>(acc[i][0], t34, v.x);
+        acc[i][1] = tap_acc2<MODE>(acc[i][1], t56, v.x);
+      }
+    }
+    if (xo >= nx) continue;
+    const i64 rb = row0 + 32 * c + w * XS_RR;
+    i64 iz = 0;
+    int iy = 0;
+    if (ep.dx) {
+      iz = (i64)((unsigned long long)rb / (unsigned)ny);
+      iy = (int)(rb - iz * ny);
+    }
+#pragma unroll
+    for (int i = 0; i < XS_RR; i++) {
+      const i64 row = rb + i;
+      if (row >= nrows) break;
+      float r4[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
+      const i64 o = row * (i64)nx + xo;
+      if (ep.dx) {
+        while (iy >= ny) { iy -= ny; iz++; }
+        const float dy = __ldg(ep.dy + iy), dz = __ldg(ep.dz + iz);
+        iy++;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          // filter3d.hpp:1016-1019: den = (dx*dy)*dz, IEEE division
+          const float den = __fmul_rn(__fmul_rn(dxv[e], dy), dz);
+          r4[e] = __fdiv_rn(r4[e], den);
+        }
+      } else if (ep.den3) {
+        const float4 den = ld4(ep.den3 + o);
+        if (den.x > 0.0f) r4[0] = __fdiv_rn(r4[0], den.x);  // filter3d.hpp:991-992
+        if (den.y > 0.0f) r4[1] = __fdiv_rn(r4[1], den.y);
+        if (den.z > 0.0f) r4[2] = __fdiv_rn(r4[2], den.z);
+        if (den.w > 0.0f) r4[3] = __fdiv_rn(r4[3], den.w);
+      }
+      if (ep.minuend) {
+        const float4 mn = ld4(ep.minuend + o);
+        r4[0] = __fmul_rn(__fsub_rn(mn.x, r4[0]), ep.scale);
+        r4[1] = __fmul_rn(__fsub_rn(mn.y, r4[1]), ep.scale);
+        r4[2] = __fmul_rn(__fsub_rn(mn.z, r4[2]), ep.scale);
+        r4[3] = __fmul_rn(__fsub_rn(mn.w, r4[3]), ep.scale);
+      }
+      *reinterpret_cast<float4 *>(out + o) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+    }
+  }
+}
+
 __global__ void fill_kernel(float *p, float v, i64 n) {
   i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   i64 stride = (i64)gridDim.x * blockDim.x;
@@ -362,9 +727,59 @@ static void launch_axis_mode(visfd_ctx *ctx, const float *in, float *out, const 
   ctx->count_launch();
 }
 
+template <int MODE>
+static void launch_axis2_mode(visfd_ctx *ctx, const float *in, float *out, const float *d_taps, int hw,
+                              i64 nx, i64 n_axis, i64 s_axis, i64 n_other, i64 s_other) {
+  const int ntap8 = (2 * hw + 1 + 7) & ~7;
+  const size_t smem = ((size_t)(ntap8 + A2_S - 1) * AX_TX + ntap8) * sizeof(float);
+  VREQUIRE(smem <= 220 * 1024, "filter half-width too large for the sweep kernel");
+  VREQUIRE(n_other <= 65535 && div_up(n_axis, A2_S) <= 65535, "volume too large in y/z for one launch");
+  static bool attr_set = false;
+  if (!attr_set) {
+    VCK(cudaFuncSetAttribute(sweep_axis2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  dim3 grid(div_up(nx, AX_TX), div_up(n_axis, A2_S), (unsigned)n_other);
+  dim3 block(32, 8);
+  sweep_axis2_kernel<MODE><<<grid, block, smem, ctx->stream>>>(in, out, d_taps, hw, ntap8, (int)nx, n_axis,
+                                                               s_axis, s_other, vec_ok);
+  VCK(cudaGetLastError());
+  ctx->count_launch();
+}
+
+template <int MODE>
+static bool launch_axis3_mode(visfd_ctx *ctx, const float *in, float *out, const float *d_taps, int hw,
+                              i64 nx, i64 n_axis, i64 s_axis, i64 n_other, i64 s_other) {
+  const int ntap8 = (2 * hw + 1 + 7) & ~7;
+  const size_t smem = ((size_t)(ntap8 - 1 + A3_NCH * A2_S) * AX_TX + ntap8) * sizeof(float);
+  const bool vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  if (!vec_ok || smem > 100 * 1024 || n_other > 65535 || div_up(n_axis, A3_NCH * A2_S) > 65535) return false;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(div_up(nx, AX_TX), div_up(n_axis, A3_NCH * A2_S), (unsigned)n_other);
+  dim3 block(32, 8);
+  sweep_axis3_kernel<MODE><<<grid, block, smem, ctx->stream>>>(in, out, d_taps, hw, ntap8, (int)nx, n_axis,
+                                                               s_axis, s_other);
+  VCK(cudaGetLastError());
+  ctx->count_launch();
+  return true;
+}
+
 static void launch_axis(visfd_ctx *ctx, const float *in, float *out, const float *mask,
                         const float *d_taps, int hw, i64 nx, i64 n_axis, i64 s_axis,
                         i64 n_other, i64 s_other) {
+  if (!mask) {
+    if (ctx->fast_gauss ? launch_axis3_mode<MODE_FAST>(ctx, in, out, d_taps, hw, nx, n_axis, s_axis, n_other, s_other)
+                        : launch_axis3_mode<MODE_EXACT>(ctx, in, out, d_taps, hw, nx, n_axis, s_axis, n_other, s_other))
+      return;
+    if (ctx->fast_gauss) launch_axis2_mode<MODE_FAST>(ctx, in, out, d_taps, hw, nx, n_axis, s_axis, n_other, s_other);
+    else launch_axis2_mode<MODE_EXACT>(ctx, in, out, d_taps, hw, nx, n_axis, s_axis, n_other, s_other);
+    return;
+  }
   if (ctx->fast_gauss)
     launch_axis_mode<MODE_FAST>(ctx, in, out, mask, d_taps, hw, nx, n_axis, s_axis, n_other, s_other);
   else if (mask)
@@ -385,7 +800,29 @@ static void launch_x(visfd_ctx *ctx, const float *in, float *out, const float *d
     VCK(cudaFuncSetAttribute(sweep_x_kernel<MODE_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
-  int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0) &&
+               (!ep.den3 || ((uintptr_t)ep.den3 & 15) == 0) && (!ep.minuend || ((uintptr_t)ep.minuend & 15) == 0);
+  {
+    // pipelined kernel: 1-D grid, x tiles fastest
+    const size_t smem2 = ((size_t)X2_ROWS * pitch + 2 * (2 * hw + 1 + 40)) * sizeof(float);
+    const i64 nxt = div_up(nx, XS_TX), nrt = (nrows + X2_ROWS - 1) / X2_ROWS;
+    if (vec_ok && smem2 <= 100 * 1024 && nxt * nrt <= 2147483647LL) {
+      static bool attr2 = false;
+      if (!attr2) {
+        VCK(cudaFuncSetAttribute(sweep_x2_kernel<MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        VCK(cudaFuncSetAttribute(sweep_x2_kernel<MODE_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr2 = true;
+      }
+      const unsigned grid = (unsigned)(nxt * nrt);
+      if (ctx->fast_gauss)
+        sweep_x2_kernel<MODE_FAST><<<grid, 256, smem2, ctx->stream>>>(in, out, d_taps, hw, (int)nx, nrows, (int)ny, (int)nxt, ep);
+      else
+        sweep_x2_kernel<MODE_EXACT><<<grid, 256, smem2, ctx->stream>>>(in, out, d_taps, hw, (int)nx, nrows, (int)ny, (int)nxt, ep);
+      VCK(cudaGetLastError());
+      ctx->count_launch();
+      return;
+    }
+  }
   // rows go on grid.x (2^31-1 blocks), x tiles on grid.y
   i64 gx = (nrows + XS_ROWS - 1) / XS_ROWS;
   VREQUIRE(gx <= 2147483647LL && div_up(nx, XS_TX) <= 65535, "volume too large for one launch");
