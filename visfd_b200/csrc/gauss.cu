@@ -370,20 +370,26 @@ sweep_axis3_kernel(const float *__restrict__ in, float *__restrict__ out,
   const i64 base = (i64)blockIdx.z * s_other;
   const i64 lo = A0 + hw - ntap8 + 1;          // tile row rho holds input position lo + rho
   const bool xin = xl < nx;
+  // every thread copies its 16-byte column of rows wy, wy+8, ...: one pointer increment per copy
+  const float *colbase = in + base + xl;
 #pragma unroll
   for (int c = 0; c < A3_NCH; c++) {
     const int r_begin = c == 0 ? 0 : ntap8 - 1 + A2_S * c, r_end = ntap8 - 1 + A2_S * (c + 1);
     if (A0 + A2_S * c < n_axis) {
+      i64 a = lo + r_begin + wy;
+      const float *src = colbase + a * s_axis;
+      float *dst = tile + (size_t)(r_begin + wy) * AX_TX + 4 * lane;
       for (int r = r_begin + wy; r < r_end; r += 8) {
-        const i64 a = lo + r;
         const bool ok = xin && a >= 0 && a < n_axis;
-        cp_async16_zfill(tile + (size_t)r * AX_TX + 4 * lane, ok ? in + base + a * s_axis + xl : in, ok);
+        cp_async16_zfill(dst, ok ? src : in, ok);
+        a += 8;
+        src += 8 * s_axis;
+        dst += 8 * AX_TX;
       }
     }
     cp_async_commit_group();
   }
-  const int ntap = 2 * hw + 1;
-  for (int k = tid; k < ntap8; k += 256) tp[k] = (k < ntap) ? taps[k] : 0.0f;
+  if (tid < ntap8) tp[tid] = (tid < 2 * hw + 1) ? taps[tid] : 0.0f;   // ntap8 <= 256 (checked by the host)
 
 #pragma unroll 1
   for (int c = 0; c < A3_NCH; c++) {
@@ -567,7 +573,40 @@ sweep_x_kernel(const float *__restrict__ in, float *__restrict__ out,
 // integer division per thread instead of two 64-bit ones per row.
 constexpr int X2_ROWS = 64;
 
-template <int MODE>
+// One step of the X sweep: the aligned input float4 at column offset 4m feeds the four
+// outputs of the thread through taps t[e - c + 3].  POS 1 / 2 = the highest / lowest step,
+// where the taps outside [0, 2hw] are known at compile time from DELTA = hwpad - hw and the
+// packed operations that would only multiply zero taps are dropped.
+template <int MODE, int DELTA, int POS>
+__device__ __forceinline__ void x2_step(float2 (&acc)[XS_RR][2], const float *tb0, const float *tb1,
+                                        const float *trow, int pitch, int m) {
+  // tap pairs (t[j], t[j+1]): even j from tp, odd j from the shifted copy
+  const float4 e0 = *reinterpret_cast<const float4 *>(tb0 - 4 * m);      // t0 t1 t2 t3
+  const float4 e1 = *reinterpret_cast<const float4 *>(tb0 - 4 * m + 4);  // t4 t5 t6 .
+  const float4 o0 = *reinterpret_cast<const float4 *>(tb1 - 4 * m);      // t1 t2 t3 t4
+  const float4 o1 = *reinterpret_cast<const float4 *>(tb1 - 4 * m + 4);  // t5 t6 . .
+  const float2 t01 = make_float2(e0.x, e0.y), t23 = make_float2(e0.z, e0.w), t45 = make_float2(e1.x, e1.y);
+  const float2 t12 = make_float2(o0.x, o0.y), t34 = make_float2(o0.z, o0.w), t56 = make_float2(o1.x, o1.y);
+  // pair p (outputs 2p, 2p+1) and input column c are live unless both taps are out of range
+#define X2_LIVE(p, c) (POS == 0 || (POS == 1 ? (2 * (p) + 1 - (c) >= DELTA) : (2 * (p) - (c) <= -DELTA)))
+#pragma unroll
+  for (int i = 0; i < XS_RR; i++) {
+    const float4 v = *reinterpret_cast<const float4 *>(trow + (size_t)i * pitch + 4 * m);
+    // output e takes tap t[e - c + 3] from input column c; c descending = taps ascending
+    if (X2_LIVE(0, 3)) acc[i][0] = tap_acc2<MODE>(acc[i][0], t01, v.w);
+    if (X2_LIVE(1, 3)) acc[i][1] = tap_acc2<MODE>(acc[i][1], t23, v.w);
+    if (X2_LIVE(0, 2)) acc[i][0] = tap_acc2<MODE>(acc[i][0], t12, v.z);
+    if (X2_LIVE(1, 2)) acc[i][1] = tap_acc2<MODE>(acc[i][1], t34, v.z);
+    if (X2_LIVE(0, 1)) acc[i][0] = tap_acc2<MODE>(acc[i][0], t23, v.y);
+    if (X2_LIVE(1, 1)) acc[i][1] = tap_acc2<MODE>(acc[i][1], t45, v.y);
+    if (X2_LIVE(0, 0)) acc[i][0] = tap_acc2<MODE>(acc[i][0], t34, v.x);
+    if (X2_LIVE(1, 0)) acc[i][1] = tap_acc2<MODE>(acc[i][1], t56, v.x);
+  }
+#undef X2_LIVE
+}
+
+// EPI: 0 = no normalisation, 1 = divide by the product of the edge profiles, 2 = divide by den3
+template <int MODE, int DELTA, int EPI>
 __global__ void __launch_bounds__(256, 3)
 sweep_x2_kernel(const float *__restrict__ in, float *__restrict__ out,
                 const float *__restrict__ taps, int hw, int nx, i64 nrows, int ny, int nxt,
@@ -583,16 +622,24 @@ sweep_x2_kernel(const float *__restrict__ in, float *__restrict__ out,
   const i64 row0 = (i64)(blockIdx.x / nxt) * X2_ROWS;
   const int x0 = xt * XS_TX;
   const int nvec = (XS_TX + 2 * hwpad) >> 2;
+  // every thread copies a fixed 16-byte column of the tile (two of them for the few that
+  // cover the halo) in rows w, w+8, ...: one pointer increment per copy
 #pragma unroll
   for (int c = 0; c < 2; c++) {
     if (row0 + 32 * c < nrows) {
-      for (int r = 32 * c + w; r < 32 * c + 32; r += 8) {
-        const i64 row = row0 + r;
-        const float *prow = in + row * (i64)nx;
-        for (int cc = lane; cc < nvec; cc += 32) {
-          const int x = x0 - hwpad + 4 * cc;
-          const bool ok = row < nrows && x >= 0 && x < nx;
-          cp_async16_zfill(tile + (size_t)r * pitch + 4 * cc, ok ? prow + x : in, ok);
+      for (int cc = lane; cc < nvec; cc += 32) {
+        const int x = x0 - hwpad + 4 * cc;
+        const bool okx = x >= 0 && x < nx;
+        i64 row = row0 + 32 * c + w;
+        const float *src = okx ? in + row * (i64)nx + x : in;
+        float *dst = tile + (size_t)(32 * c + w) * pitch + 4 * cc;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const bool ok = okx && row < nrows;
+          cp_async16_zfill(dst, ok ? src : in, ok);
+          row += 8;
+          src += 8 * (i64)nx;
+          dst += 8 * pitch;
         }
       }
     }
@@ -614,7 +661,7 @@ sweep_x2_kernel(const float *__restrict__ in, float *__restrict__ out,
   const float *tb1 = tp1 + P + hw + hwpad - 3;
   const int xo = x0 + 4 * lane;
   float dxv[4] = {1.f, 1.f, 1.f, 1.f};
-  if (ep.dx && xo < nx) {
+  if (EPI == 1 && xo < nx) {
 #pragma unroll
     for (int e = 0; e < 4; e++) dxv[e] = __ldg(ep.dx + xo + e);
   }
@@ -629,67 +676,57 @@ sweep_x2_kernel(const float *__restrict__ in, float *__restrict__ out,
     for (int i = 0; i < XS_RR; i++) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
     const float *trow = tile + (size_t)(32 * c + w * XS_RR) * pitch + 4 * lane;
     // highest input column first = the reference's accumulation order (tap index ascending)
-    for (int m = nsteps - 1; m >= 0; m--) {
-      // tap pairs (t[j], t[j+1]): even j from tp, odd j from the shifted copy
-      const float4 e0 = *reinterpret_cast<const float4 *>(tb0 - 4 * m);      // t0 t1 t2 t3
-      const float4 e1 = *reinterpret_cast<const float4 *>(tb0 - 4 * m + 4);  // t4 t5 t6 .
-      const float4 o0 = *reinterpret_cast<const float4 *>(tb1 - 4 * m);      // t1 t2 t3 t4
-      const float4 o1 = *reinterpret_cast<const float4 *>(tb1 - 4 * m + 4);  // t5 t6 . .
-      const float2 t01 = make_float2(e0.x, e0.y), t23 = make_float2(e0.z, e0.w), t45 = make_float2(e1.x, e1.y);
-      const float2 t12 = make_float2(o0.x, o0.y), t34 = make_float2(o0.z, o0.w), t56 = make_float2(o1.x, o1.y);
-#pragma unroll
-      for (int i = 0; i < XS_RR; i++) {
-        const float4 v = *reinterpret_cast<const float4 *>(trow + (size_t)i * pitch + 4 * m);
-        // output e takes tap t[e - c + 3] from input column c; c descending = taps ascending
-        acc[i][0] = tap_acc2<MODE>(acc[i][0], t01, v.w);
-        acc[i][1] = tap_acc2<MODE>(acc[i][1], t23, v.w);
-        acc[i][0] = tap_acc2<MODE>(acc[i][0], t12, v.z);
-        acc[i][1] = tap_acc2<MODE>(acc[i][1], t34, v.z);
-        acc[i][0] = tap_acc2<MODE>(acc[i][0], t23, v.y);
-        acc[i][1] = tap_acc2<MODE>(acc[i][1], t45, v.y);
-        acc[i][0] = tap_acc2<MODE>(acc[i][0], t34, v.x);
-        acc[i][1] = tap_acc2<MODE>(acc[i][1], t56, v.x);
-      }
+    if (nsteps >= 2) {
+      x2_step<MODE, DELTA, 1>(acc, tb0, tb1, trow, pitch, nsteps - 1);
+      for (int m = nsteps - 2; m >= 1; m--) x2_step<MODE, DELTA, 0>(acc, tb0, tb1, trow, pitch, m);
+      x2_step<MODE, DELTA, 2>(acc, tb0, tb1, trow, pitch, 0);
+    } else {
+      x2_step<MODE, DELTA, 0>(acc, tb0, tb1, trow, pitch, 0);
     }
     if (xo >= nx) continue;
     const i64 rb = row0 + 32 * c + w * XS_RR;
-    i64 iz = 0;
-    int iy = 0;
-    if (ep.dx) {
-      iz = (i64)((unsigned long long)rb / (unsigned)ny);
-      iy = (int)(rb - iz * ny);
+    unsigned iz = 0, iy = 0;
+    if (EPI == 1) {   // rows < 2^32 (checked by the host)
+      iz = (unsigned)rb / (unsigned)ny;
+      iy = (unsigned)rb - iz * (unsigned)ny;
     }
+    const i64 o0 = rb * (i64)nx + xo;
+    float *op = out + o0;
+    const float *mp = ep.minuend ? ep.minuend + o0 : nullptr;
+    const float *dp = EPI == 2 ? ep.den3 + o0 : nullptr;
+    const int nrow_here = (int)min((i64)XS_RR, nrows - rb);
 #pragma unroll
     for (int i = 0; i < XS_RR; i++) {
-      const i64 row = rb + i;
-      if (row >= nrows) break;
+      if (i >= nrow_here) break;
       float r4[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
-      const i64 o = row * (i64)nx + xo;
-      if (ep.dx) {
-        while (iy >= ny) { iy -= ny; iz++; }
+      if (EPI == 1) {
+        while (iy >= (unsigned)ny) { iy -= ny; iz++; }
         const float dy = __ldg(ep.dy + iy), dz = __ldg(ep.dz + iz);
         iy++;
+        // filter3d.hpp:1016-1019: den = (dx*dy)*dz, IEEE division.  x / 1 == x, so the
+        // interior is skipped whenever the taps sum to exactly 1 (one test per row).
+        float den[4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          // filter3d.hpp:1016-1019: den = (dx*dy)*dz, IEEE division
-          const float den = __fmul_rn(__fmul_rn(dxv[e], dy), dz);
-          r4[e] = __fdiv_rn(r4[e], den);
+        for (int e = 0; e < 4; e++) den[e] = __fmul_rn(__fmul_rn(dxv[e], dy), dz);
+        if (!(den[0] == 1.0f && den[1] == 1.0f && den[2] == 1.0f && den[3] == 1.0f)) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) r4[e] = __fdiv_rn(r4[e], den[e]);
         }
-      } else if (ep.den3) {
-        const float4 den = ld4(ep.den3 + o);
+      } else if (EPI == 2) {
+        const float4 den = ld4(dp + (size_t)i * nx);
         if (den.x > 0.0f) r4[0] = __fdiv_rn(r4[0], den.x);  // filter3d.hpp:991-992
         if (den.y > 0.0f) r4[1] = __fdiv_rn(r4[1], den.y);
         if (den.z > 0.0f) r4[2] = __fdiv_rn(r4[2], den.z);
         if (den.w > 0.0f) r4[3] = __fdiv_rn(r4[3], den.w);
       }
-      if (ep.minuend) {
-        const float4 mn = ld4(ep.minuend + o);
+      if (mp) {
+        const float4 mn = ld4(mp + (size_t)i * nx);
         r4[0] = __fmul_rn(__fsub_rn(mn.x, r4[0]), ep.scale);
         r4[1] = __fmul_rn(__fsub_rn(mn.y, r4[1]), ep.scale);
         r4[2] = __fmul_rn(__fsub_rn(mn.z, r4[2]), ep.scale);
         r4[3] = __fmul_rn(__fsub_rn(mn.w, r4[3]), ep.scale);
       }
-      *reinterpret_cast<float4 *>(out + o) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+      *reinterpret_cast<float4 *>(op + (size_t)i * nx) = make_float4(r4[0], r4[1], r4[2], r4[3]);
     }
   }
 }
@@ -754,7 +791,7 @@ static bool launch_axis3_mode(visfd_ctx *ctx, const float *in, float *out, const
   const int ntap8 = (2 * hw + 1 + 7) & ~7;
   const size_t smem = ((size_t)(ntap8 - 1 + A3_NCH * A2_S) * AX_TX + ntap8) * sizeof(float);
   const bool vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
-  if (!vec_ok || smem > 100 * 1024 || n_other > 65535 || div_up(n_axis, A3_NCH * A2_S) > 65535) return false;
+  if (!vec_ok || smem > 100 * 1024 || ntap8 > 256 || n_other > 65535 || div_up(n_axis, A3_NCH * A2_S) > 65535) return false;
   static bool attr_set = false;
   if (!attr_set) {
     VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -806,18 +843,30 @@ static void launch_x(visfd_ctx *ctx, const float *in, float *out, const float *d
     // pipelined kernel: 1-D grid, x tiles fastest
     const size_t smem2 = ((size_t)X2_ROWS * pitch + 2 * (2 * hw + 1 + 40)) * sizeof(float);
     const i64 nxt = div_up(nx, XS_TX), nrt = (nrows + X2_ROWS - 1) / X2_ROWS;
-    if (vec_ok && smem2 <= 100 * 1024 && nxt * nrt <= 2147483647LL) {
-      static bool attr2 = false;
-      if (!attr2) {
-        VCK(cudaFuncSetAttribute(sweep_x2_kernel<MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        VCK(cudaFuncSetAttribute(sweep_x2_kernel<MODE_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr2 = true;
-      }
+    if (vec_ok && smem2 <= 100 * 1024 && nxt * nrt <= 2147483647LL && nrows < 4294967296LL) {
       const unsigned grid = (unsigned)(nxt * nrt);
-      if (ctx->fast_gauss)
-        sweep_x2_kernel<MODE_FAST><<<grid, 256, smem2, ctx->stream>>>(in, out, d_taps, hw, (int)nx, nrows, (int)ny, (int)nxt, ep);
-      else
-        sweep_x2_kernel<MODE_EXACT><<<grid, 256, smem2, ctx->stream>>>(in, out, d_taps, hw, (int)nx, nrows, (int)ny, (int)nxt, ep);
+#define X2_LAUNCH_E(M, D, E)                                                                                  \
+      do {                                                                                                    \
+        VCK(cudaFuncSetAttribute(sweep_x2_kernel<M, D, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+        sweep_x2_kernel<M, D, E><<<grid, 256, smem2, ctx->stream>>>(in, out, d_taps, hw, (int)nx, nrows, (int)ny, (int)nxt, ep); \
+      } while (0)
+#define X2_LAUNCH(M, D)                                  \
+      do {                                               \
+        if (ep.dx) X2_LAUNCH_E(M, D, 1);                 \
+        else if (ep.den3) X2_LAUNCH_E(M, D, 2);          \
+        else X2_LAUNCH_E(M, D, 0);                       \
+      } while (0)
+#define X2_LAUNCH_D(M)                                   \
+      switch (hwpad - hw) {                              \
+        case 0: X2_LAUNCH(M, 0); break;                  \
+        case 1: X2_LAUNCH(M, 1); break;                  \
+        case 2: X2_LAUNCH(M, 2); break;                  \
+        default: X2_LAUNCH(M, 3); break;                 \
+      }
+      if (ctx->fast_gauss) { X2_LAUNCH_D(MODE_FAST) } else { X2_LAUNCH_D(MODE_EXACT) }
+#undef X2_LAUNCH_D
+#undef X2_LAUNCH
+#undef X2_LAUNCH_E
       VCK(cudaGetLastError());
       ctx->count_launch();
       return;
