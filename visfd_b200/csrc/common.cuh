@@ -47,6 +47,7 @@ struct visfd_ctx {
   int64_t launches = 0;
   int64_t last_voters = 0;
   bool fast_gauss = false;                  // FFMA sweeps instead of the bit-exact mul+add
+  bool use_tma = true;                      // stage the sweeps' tiles with TMA (VISFD_CUDA_NO_TMA=1: cp.async)
   bool timing = true;                       // record per-stage CUDA events
   std::map<std::string, double> stage_ms;   // resolved at the end of each API call
   struct PendingEvent { const char *name; cudaEvent_t a, b; };

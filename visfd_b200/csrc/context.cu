@@ -145,6 +145,8 @@ int visfd_cuda_init(int device, visfd_ctx **out) {
     c->own_stream = true;
     const char *fg = getenv("VISFD_CUDA_FAST_GAUSS");
     c->fast_gauss = fg && fg[0] == '1';
+    const char *nt = getenv("VISFD_CUDA_NO_TMA");
+    c->use_tma = !(nt && nt[0] == '1');
     *out = c;
     return 0;
   } catch (const std::exception &ex) {

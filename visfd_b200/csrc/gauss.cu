@@ -33,10 +33,81 @@
 //      Selected per context (visfd_cuda_set_fast_gauss / VISFD_CUDA_FAST_GAUSS=1).
 #include "common.cuh"
 #include "kernels.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cmath>
 #include <algorithm>
 
 namespace visfd_cuda {
+
+// ---------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor): the sweeps' shared-memory tiles are boxes of a 2-D / 3-D
+// tensor map over the volume; one thread issues the copies, the hardware zero-fills
+// everything outside the volume, and an mbarrier per chunk tells the CTA when it landed.
+// ---------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// float32 tensor of `rank` dims (x fastest), dense; box = tile extents.  false if TMA
+// cannot describe it (alignment, size) -- the caller falls back to cp.async staging.
+static bool make_tensor_map(CUtensorMap *map, const float *ptr, int rank, const i64 *dims, const int *box) {
+  PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+  if (!enc || ((uintptr_t)ptr & 15) != 0) return false;
+  cuuint64_t gdim[3], gstride[2];
+  cuuint32_t bdim[3], estr[3] = {1, 1, 1};
+  i64 stride = sizeof(float);
+  for (int d = 0; d < rank; d++) {
+    if (dims[d] <= 0 || dims[d] > 0xffffffffLL || box[d] <= 0 || box[d] > 256) return false;
+    gdim[d] = (cuuint64_t)dims[d];
+    bdim[d] = (cuuint32_t)box[d];
+    stride *= dims[d];
+    if (d + 1 < rank) {
+      if (stride % 16 != 0 || stride >= (1LL << 40)) return false;
+      gstride[d] = (cuuint64_t)stride;
+    }
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(ptr), gdim, gstride,
+                   bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
 
 // ---------------------------------------------------------------------------------
 // host: taps
@@ -143,7 +214,7 @@ __global__ void __launch_bounds__(32 * AX_WARPS)
 sweep_axis_kernel(const float *__restrict__ in, float *__restrict__ out,
                   const float *__restrict__ mask, const float *__restrict__ taps,
                   int hw, int nx, i64 n_axis, i64 s_axis, i64 s_other, int vec_ok) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int rows = AX_TA + 2 * hw + 8;          // staged rows (+8 zero rows for the unrolled tail)
   float *tile = smem;                           // [rows][AX_TX]
   float *mtile = smem + (size_t)rows * AX_TX;   // [rows][AX_TX], EXACT_MASKED only
@@ -254,7 +325,7 @@ __global__ void __launch_bounds__(256, 4)
 sweep_axis2_kernel(const float *__restrict__ in, float *__restrict__ out,
                    const float *__restrict__ taps, int hw, int ntap8, int nx, i64 n_axis,
                    i64 s_axis, i64 s_other, int vec_ok) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int rows = ntap8 + A2_S - 1;
   float *tile = smem;                          // [rows][AX_TX]
   float *tp = smem + (size_t)rows * AX_TX;     // [ntap8]
@@ -354,27 +425,51 @@ __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-template <int MODE>
+// TMA = true: the tile is fetched by cp.async.bulk.tensor boxes of 8 rows x 128 columns of
+// the 3-D tensor map `tmap` (axis_dim = 1: Y sweep, 2: Z sweep), issued by one thread and
+// tracked by one mbarrier per chunk; TMA = false: per-thread cp.async as described above.
+template <int MODE, bool TMA>
 __global__ void __launch_bounds__(256, 3)
-sweep_axis3_kernel(const float *__restrict__ in, float *__restrict__ out,
+sweep_axis3_kernel(const __grid_constant__ CUtensorMap tmap, int axis_dim,
+                   const float *__restrict__ in, float *__restrict__ out,
                    const float *__restrict__ taps, int hw, int ntap8, int nx, i64 n_axis,
                    i64 s_axis, i64 s_other) {
-  extern __shared__ __align__(16) float smem[];
-  const int rows = ntap8 - 1 + A3_NCH * A2_S;
+  extern __shared__ __align__(128) float smem[];
+  const int rows = ntap8 + A3_NCH * A2_S;      // multiple of 8
   float *tile = smem;                          // [rows][AX_TX]
   float *tp = smem + (size_t)rows * AX_TX;     // [ntap8]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tp + ntap8);   // [A3_NCH], TMA only
   const int lane = threadIdx.x, wy = threadIdx.y;
   const int tid = wy * 32 + lane;
   const int xl = blockIdx.x * AX_TX + 4 * lane;
   const i64 A0 = (i64)blockIdx.y * (A3_NCH * A2_S);
   const i64 base = (i64)blockIdx.z * s_other;
-  const i64 lo = A0 + hw - ntap8 + 1;          // tile row rho holds input position lo + rho
+  const i64 lo = A0 + hw - ntap8;              // tile row rho holds input position lo + rho
   const bool xin = xl < nx;
+  if (TMA) {
+    if (tid == 0) {
+#pragma unroll
+      for (int c = 0; c < A3_NCH; c++) mbar_init(bars + c, 1);
+      mbar_init_fence();
+#pragma unroll
+      for (int c = 0; c < A3_NCH; c++) {
+        if (A0 + A2_S * c >= n_axis) break;
+        const int r_begin = c == 0 ? 0 : ntap8 + A2_S * c, r_end = ntap8 + A2_S * (c + 1);
+        mbar_expect_tx(bars + c, (unsigned)(r_end - r_begin) * AX_TX * sizeof(float));
+        for (int r = r_begin; r < r_end; r += 8) {
+          const int a = (int)(lo + r), o = (int)blockIdx.z;
+          tma_load_3d(tile + (size_t)r * AX_TX, &tmap, bars + c, blockIdx.x * AX_TX, axis_dim == 1 ? a : o,
+                      axis_dim == 1 ? o : a);
+        }
+      }
+    }
+  }
   // every thread copies its 16-byte column of rows wy, wy+8, ...: one pointer increment per copy
   const float *colbase = in + base + xl;
 #pragma unroll
   for (int c = 0; c < A3_NCH; c++) {
-    const int r_begin = c == 0 ? 0 : ntap8 - 1 + A2_S * c, r_end = ntap8 - 1 + A2_S * (c + 1);
+    if (TMA) break;
+    const int r_begin = c == 0 ? 0 : ntap8 + A2_S * c, r_end = ntap8 + A2_S * (c + 1);
     if (A0 + A2_S * c < n_axis) {
       i64 a = lo + r_begin + wy;
       const float *src = colbase + a * s_axis;
@@ -390,18 +485,23 @@ sweep_axis3_kernel(const float *__restrict__ in, float *__restrict__ out,
     cp_async_commit_group();
   }
   if (tid < ntap8) tp[tid] = (tid < 2 * hw + 1) ? taps[tid] : 0.0f;   // ntap8 <= 256 (checked by the host)
+  if (TMA) __syncthreads();   // barriers initialised, taps staged
 
 #pragma unroll 1
   for (int c = 0; c < A3_NCH; c++) {
     if (A0 + A2_S * c >= n_axis) break;   // uniform
-    if (c == 0) cp_async_wait_group<A3_NCH - 1>();
-    else if (c == 1) cp_async_wait_group<A3_NCH - 2>();
-    else cp_async_wait_group<0>();
-    __syncthreads();
+    if (TMA) {
+      mbar_wait(bars + c, 0);
+    } else {
+      if (c == 0) cp_async_wait_group<A3_NCH - 1>();
+      else if (c == 1) cp_async_wait_group<A3_NCH - 2>();
+      else cp_async_wait_group<0>();
+      __syncthreads();
+    }
     float2 acc[A2_R][2];
 #pragma unroll
     for (int r = 0; r < A2_R; r++) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
-    const float *row0 = tile + (size_t)(A2_S * c + A2_R * wy + ntap8 - 1) * AX_TX + 4 * lane;
+    const float *row0 = tile + (size_t)(A2_S * c + A2_R * wy + ntap8) * AX_TX + 4 * lane;
 #define ROW(k) (*reinterpret_cast<const float4 *>(row0 - (ptrdiff_t)(k) * AX_TX))
     float4 win[8];
     win[5] = ROW(-3);
@@ -459,7 +559,7 @@ __global__ void __launch_bounds__(256)
 sweep_x_kernel(const float *__restrict__ in, float *__restrict__ out,
                const float *__restrict__ taps, int hw, int nx, i64 nrows, int ny,
                XEpilogue ep, int vec_ok) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int hwpad = (hw + 3) & ~3;
   const int pitch = XS_TX + 2 * hwpad + 4;   // +4: keeps rows 16 B aligned, staggers banks
   float *tile = smem;                        // [XS_ROWS][pitch]
@@ -611,7 +711,7 @@ __global__ void __launch_bounds__(256, 3)
 sweep_x2_kernel(const float *__restrict__ in, float *__restrict__ out,
                 const float *__restrict__ taps, int hw, int nx, i64 nrows, int ny, int nxt,
                 XEpilogue ep) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int hwpad = (hw + 3) & ~3;
   const int pitch = XS_TX + 2 * hwpad + 4;
   float *tile = smem;                        // [X2_ROWS][pitch]
@@ -789,18 +889,30 @@ template <int MODE>
 static bool launch_axis3_mode(visfd_ctx *ctx, const float *in, float *out, const float *d_taps, int hw,
                               i64 nx, i64 n_axis, i64 s_axis, i64 n_other, i64 s_other) {
   const int ntap8 = (2 * hw + 1 + 7) & ~7;
-  const size_t smem = ((size_t)(ntap8 - 1 + A3_NCH * A2_S) * AX_TX + ntap8) * sizeof(float);
+  const size_t smem = ((size_t)(ntap8 + A3_NCH * A2_S) * AX_TX + ntap8) * sizeof(float) + A3_NCH * sizeof(uint64_t);
   const bool vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
   if (!vec_ok || smem > 100 * 1024 || ntap8 > 256 || n_other > 65535 || div_up(n_axis, A3_NCH * A2_S) > 65535) return false;
   static bool attr_set = false;
   if (!attr_set) {
-    VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
   dim3 grid(div_up(nx, AX_TX), div_up(n_axis, A3_NCH * A2_S), (unsigned)n_other);
   dim3 block(32, 8);
-  sweep_axis3_kernel<MODE><<<grid, block, smem, ctx->stream>>>(in, out, d_taps, hw, ntap8, (int)nx, n_axis,
-                                                               s_axis, s_other);
+  // the volume as a 3-D tensor (x, y, z): Y sweep: s_axis == nx; Z sweep: s_other == nx
+  const int axis_dim = (s_axis == nx) ? 1 : 2;
+  const i64 dims[3] = {nx, axis_dim == 1 ? n_axis : n_other, axis_dim == 1 ? n_other : n_axis};
+  const int box[3] = {AX_TX, axis_dim == 1 ? 8 : 1, axis_dim == 1 ? 1 : 8};
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  const bool consistent = axis_dim == 1 ? (s_other == nx * n_axis) : (s_axis == nx * n_other);
+  if (ctx->use_tma && consistent && make_tensor_map(&tmap, in, 3, dims, box))
+    sweep_axis3_kernel<MODE, true><<<grid, block, smem, ctx->stream>>>(tmap, axis_dim, in, out, d_taps, hw, ntap8,
+                                                                      (int)nx, n_axis, s_axis, s_other);
+  else
+    sweep_axis3_kernel<MODE, false><<<grid, block, smem, ctx->stream>>>(tmap, axis_dim, in, out, d_taps, hw, ntap8,
+                                                                       (int)nx, n_axis, s_axis, s_other);
   VCK(cudaGetLastError());
   ctx->count_launch();
   return true;
