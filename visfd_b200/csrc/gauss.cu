@@ -706,26 +706,40 @@ __device__ __forceinline__ void x2_step(float2 (&acc)[XS_RR][2], const float *tb
 }
 
 // EPI: 0 = no normalisation, 1 = divide by the product of the edge profiles, 2 = divide by den3
-template <int MODE, int DELTA, int EPI>
+// TMA: the two 32-row chunks are boxes (128 + 2 hwpad) x 32 of the 2-D tensor map (x, row).
+template <int MODE, int DELTA, int EPI, bool TMA>
 __global__ void __launch_bounds__(256, 3)
-sweep_x2_kernel(const float *__restrict__ in, float *__restrict__ out,
+sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ in, float *__restrict__ out,
                 const float *__restrict__ taps, int hw, int nx, i64 nrows, int ny, int nxt,
                 XEpilogue ep) {
   extern __shared__ __align__(128) float smem[];
   const int hwpad = (hw + 3) & ~3;
-  const int pitch = XS_TX + 2 * hwpad + 4;
+  const int pitch = XS_TX + 2 * hwpad + (TMA ? 0 : 4);
   float *tile = smem;                        // [X2_ROWS][pitch]
-  float *tp = smem + (size_t)X2_ROWS * pitch;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)X2_ROWS * pitch);   // [2] (+2 pad), TMA only
+  float *tp = smem + (size_t)X2_ROWS * pitch + 8;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int tid = threadIdx.x;
   const int xt = blockIdx.x % nxt;
   const i64 row0 = (i64)(blockIdx.x / nxt) * X2_ROWS;
   const int x0 = xt * XS_TX;
   const int nvec = (XS_TX + 2 * hwpad) >> 2;
-  // every thread copies a fixed 16-byte column of the tile (two of them for the few that
-  // cover the halo) in rows w, w+8, ...: one pointer increment per copy
+  if (TMA && tid == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    mbar_init_fence();
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      if (row0 + 32 * c >= nrows) break;
+      mbar_expect_tx(bars + c, 32u * (unsigned)pitch * sizeof(float));
+      tma_load_2d(tile + (size_t)32 * c * pitch, &tmap, bars + c, x0 - hwpad, (int)(row0 + 32 * c));
+    }
+  }
+  // (cp.async) every thread copies a fixed 16-byte column of the tile (two of them for the
+  // few that cover the halo) in rows w, w+8, ...: one pointer increment per copy
 #pragma unroll
   for (int c = 0; c < 2; c++) {
+    if (TMA) break;
     if (row0 + 32 * c < nrows) {
       for (int cc = lane; cc < nvec; cc += 32) {
         const int x = x0 - hwpad + 4 * cc;
@@ -769,8 +783,13 @@ sweep_x2_kernel(const float *__restrict__ in, float *__restrict__ out,
 #pragma unroll 1
   for (int c = 0; c < 2; c++) {
     if (row0 + 32 * c >= nrows) break;  // uniform
-    if (c == 0) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
-    __syncthreads();
+    if (TMA) {
+      if (c == 0) __syncthreads();   // barriers initialised, taps staged
+      mbar_wait(bars + c, 0);
+    } else {
+      if (c == 0) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
+      __syncthreads();
+    }
     float2 acc[XS_RR][2];   // outputs (0,1) and (2,3) of each row
 #pragma unroll
     for (int i = 0; i < XS_RR; i++) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
@@ -953,14 +972,21 @@ static void launch_x(visfd_ctx *ctx, const float *in, float *out, const float *d
                (!ep.den3 || ((uintptr_t)ep.den3 & 15) == 0) && (!ep.minuend || ((uintptr_t)ep.minuend & 15) == 0);
   {
     // pipelined kernel: 1-D grid, x tiles fastest
-    const size_t smem2 = ((size_t)X2_ROWS * pitch + 2 * (2 * hw + 1 + 40)) * sizeof(float);
+    const size_t smem2 = ((size_t)X2_ROWS * pitch + 8 + 2 * (2 * hw + 1 + 40)) * sizeof(float);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const i64 dims2[2] = {nx, nrows};
+    const int box2[2] = {XS_TX + 2 * hwpad, 32};
+    const bool tma = ctx->use_tma && make_tensor_map(&tmap, in, 2, dims2, box2);
     const i64 nxt = div_up(nx, XS_TX), nrt = (nrows + X2_ROWS - 1) / X2_ROWS;
     if (vec_ok && smem2 <= 100 * 1024 && nxt * nrt <= 2147483647LL && nrows < 4294967296LL) {
       const unsigned grid = (unsigned)(nxt * nrt);
 #define X2_LAUNCH_E(M, D, E)                                                                                  \
       do {                                                                                                    \
-        VCK(cudaFuncSetAttribute(sweep_x2_kernel<M, D, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
-        sweep_x2_kernel<M, D, E><<<grid, 256, smem2, ctx->stream>>>(in, out, d_taps, hw, (int)nx, nrows, (int)ny, (int)nxt, ep); \
+        VCK(cudaFuncSetAttribute(sweep_x2_kernel<M, D, E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+        VCK(cudaFuncSetAttribute(sweep_x2_kernel<M, D, E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+        if (tma) sweep_x2_kernel<M, D, E, true><<<grid, 256, smem2, ctx->stream>>>(tmap, in, out, d_taps, hw, (int)nx, nrows, (int)ny, (int)nxt, ep); \
+        else sweep_x2_kernel<M, D, E, false><<<grid, 256, smem2, ctx->stream>>>(tmap, in, out, d_taps, hw, (int)nx, nrows, (int)ny, (int)nxt, ep); \
       } while (0)
 #define X2_LAUNCH(M, D)                                  \
       do {                                               \
