@@ -247,8 +247,9 @@ __device__ __forceinline__ void voter_direction(const DirSrc &d, int nx, int ny,
   n[2] = (float)e0[2];
 }
 
+// Pass 1 of the fill (one CTA per brick): positions and weights in brick order.
 __global__ void __launch_bounds__(BR3)
-voter_fill_kernel(VoterSrc v, DirSrc d, const uint32_t *__restrict__ off, float inv_total,
+voter_fill_kernel(VoterSrc v, const uint32_t *__restrict__ off, float inv_total,
                   VoterRec *__restrict__ rec, uint32_t *__restrict__ nonpos_flag) {
   __shared__ uint32_t wsum[BR3 / 32];
   const int b = blockIdx.x;
@@ -266,17 +267,28 @@ voter_fill_kernel(VoterSrc v, DirSrc d, const uint32_t *__restrict__ off, float 
   if (!p) return;
   uint32_t rank = __popc(bal & ((1u << lane) - 1u));
   for (int k = 0; k < w; k++) rank += wsum[k];
-  float n[3];
-  voter_direction(d, v.nx, v.ny, x, y, z, n);
   const float wgt = wt * inv_total;
   if (!(wgt > 0.0f)) *nonpos_flag = 1u;  // benign race: every writer stores the same value
   // the three forms of the weight the gather kernels fold into their arithmetic (vote())
   const float w4 = 4.0f * wgt, l4 = log2f(w4);
-  VoterRec r;
-  r.a = make_float4(-(float)x, -(float)y, -(float)z, 0.5f * l4);
-  r.b = make_float4(n[0], n[1], n[2], l4);
-  r.c = make_float4(0.5f * n[0], 0.5f * n[1], 0.5f * n[2], w4);
-  rec[o0 + rank] = r;
+  VoterRec *r = rec + o0 + rank;
+  r->a = make_float4(-(float)x, -(float)y, -(float)z, 0.5f * l4);
+  r->b.w = l4;
+  r->c.w = w4;
+}
+
+// Pass 2: one THREAD per voter (dense lanes -- in the brick pass only ~5 % of the lanes are
+// voters and the double-precision eigenvector would run at that lane efficiency).
+__global__ void __launch_bounds__(256)
+voter_direction_kernel(DirSrc d, int nx, int ny, uint32_t n_voters, VoterRec *__restrict__ rec) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= n_voters) return;
+  VoterRec *r = rec + i;
+  const float4 a = r->a;
+  float n[3];
+  voter_direction(d, nx, ny, (int)(-a.x), (int)(-a.y), (i64)(-a.z), n);
+  r->b.x = n[0]; r->b.y = n[1]; r->b.z = n[2];
+  r->c.x = 0.5f * n[0]; r->c.y = 0.5f * n[1]; r->c.z = 0.5f * n[2];
 }
 
 // ---------------------------------------------------------------------------------
@@ -342,7 +354,7 @@ __device__ __forceinline__ int axis_gap(int lo_a, int hi_a, int lo_b, int hi_b) 
 }
 
 constexpr int TV_DRAIN = 32;             // voters evaluated per drain
-constexpr int TV_QCAP = 3 * TV_DRAIN;    // ring capacity (see the invariant in the kernel)
+constexpr int TV_QCAP = 5 * TV_DRAIN;    // ring capacity (see the invariant in the kernel)
 constexpr float TV_R2_EPS = 1e-30f;      // keeps 1/r^2 finite for the self vote (r = 0, d.n = 0)
 
 __device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }  // FFMA2 takes scalar (.F32) operands
@@ -449,17 +461,18 @@ __device__ __forceinline__ void drain(const VoterRec *q, int n, float fx, float 
 // tile but never synchronise with each other.  A warp
 //   1. builds the table of brick rows (contiguous ranges of the brick-ordered voter
 //      list) whose bricks can reach its patch,
-//   2. streams them 32 candidates at a time: each lane loads the position of one
-//      candidate (one batch ahead, straight from L1/L2), tests the exact distance between
+//   2. streams them 64 candidates at a time: each lane loads the positions of two
+//      candidates (one iteration ahead, straight from L1/L2), tests the exact distance between
 //      the voter and the patch box against the support radius, and -- if the voter can
 //      reach the patch -- copies its 48-byte record with cp.async into the next free slot
 //      of a warp-private shared-memory ring (slot = ballot rank),
-//   3. whenever the ring held >= 32 voters BEFORE the current batch was appended, waits
-//      for all but the newest cp.async group and drains 32 voters: every lane evaluates
-//      the voter (three broadcast LDS.128) on its two receivers.
-// Ring invariant: capacity 96, head in {0, 32, 64}; before a batch count <= 63, the
-// batch adds <= 32 (95 < 96 entries live), and a drain removes the 32 oldest, all of
-// which belong to cp.async groups older than the newest one.
+//   3. whenever the ring held >= 32 voters BEFORE the current iteration appended to it, waits
+//      for all but the newest cp.async group and drains them 32 at a time: every lane
+//      evaluates the voter (three broadcast LDS.128) on its two receivers.
+// Ring invariant: capacity 160, head a multiple of 32; an iteration tests 64 candidates.
+// Before it the ring holds <= 95 voters, it adds <= 64 (159 < 160 live), and it drains the
+// whole groups of 32 among the voters queued before it -- all of which belong to cp.async
+// groups older than the newest one -- leaving <= 31 + 64.
 template <int EXPO, bool CURVES, bool POSW, bool SHELL>
 __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(GatherArgs g) {
   extern __shared__ __align__(16) unsigned char tv_smem[];
@@ -530,53 +543,61 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
 
   // ---- 2./3. stream, cull, vote ---------------------------------------------------------
   int cur_row = 0;  // per-lane cursor into the row table (flat indices only grow)
-  auto locate = [&](uint32_t e) -> const VoterRec * {
+  auto locate = [&](uint32_t e) -> uint32_t {
     while (e >= row_pref[cur_row + 1]) cur_row++;
-    return g.rec + (row_start[cur_row] + (e - row_pref[cur_row]));
+    return row_start[cur_row] + (e - row_pref[cur_row]);
   };
   const float4 nowhere = make_float4(-1.0e9f, -1.0e9f, -1.0e9f, 0.0f);
-  int head = 0, cnt = 0;
-  const VoterRec *nrec = g.rec;
-  float4 na = nowhere;
-  if (lane < total) {
-    nrec = locate(lane);
-    na = __ldg(&nrec->a);
-  }
-  for (uint32_t base = 0; base < total; base += 32) {
-    const float4 a = na;
-    const VoterRec *rec = nrec;
-    na = nowhere;
-    if (base + 32 + lane < total) {
-      nrec = locate(base + 32 + lane);
-      na = __ldg(&nrec->a);
-    }
+  auto reach = [&](const float4 &a) -> bool {
     // exact distance from the voter (a holds the NEGATED position) to the patch box
     const float gx = fmaxf(fabsf(a.x + pcx) - 1.5f, 0.0f);
     const float gy = fmaxf(fabsf(a.y + pcy) - 1.5f, 0.0f);
     const float gz = fmaxf(fabsf(a.z + pcz) - 1.5f, 0.0f);
-    const bool pass = fmaf(gx, gx, fmaf(gy, gy, gz * gz)) < lim_pass;
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
-    const int before = cnt;
-    if (pass) {
-      int slot = head + cnt + __popc(m & ((1u << lane) - 1u));
-      if (slot >= TV_QCAP) slot -= TV_QCAP;
-      VoterRec *dst = ring + slot;
-      cp_async16(&dst->a, &rec->a);
-      cp_async16(&dst->b, &rec->b);
-      cp_async16(&dst->c, &rec->c);
-    }
+    return fmaf(gx, gx, fmaf(gy, gy, gz * gz)) < lim_pass;
+  };
+  auto enqueue = [&](int slot, uint32_t gi) {
+    if (slot >= TV_QCAP) slot -= TV_QCAP;
+    VoterRec *dst = ring + slot;
+    const VoterRec *src = g.rec + gi;
+    cp_async16(&dst->a, &src->a);
+    cp_async16(&dst->b, &src->b);
+    cp_async16(&dst->c, &src->c);
+  };
+  // Two batches of 32 candidates per iteration; their positions were requested one
+  // iteration ahead.
+  int head = 0, cnt = 0;
+  uint32_t ng0 = 0, ng1 = 0;
+  float4 na0 = nowhere, na1 = nowhere;
+  if (lane < total) { ng0 = locate(lane); na0 = __ldg(&g.rec[ng0].a); }
+  if (32 + lane < total) { ng1 = locate(32 + lane); na1 = __ldg(&g.rec[ng1].a); }
+  for (uint32_t base = 0; base < total; base += 64) {
+    const float4 a0 = na0, a1 = na1;
+    const uint32_t g0 = ng0, g1 = ng1;
+    na0 = nowhere;
+    na1 = nowhere;
+    if (base + 64 + lane < total) { ng0 = locate(base + 64 + lane); na0 = __ldg(&g.rec[ng0].a); }
+    if (base + 96 + lane < total) { ng1 = locate(base + 96 + lane); na1 = __ldg(&g.rec[ng1].a); }
+    const bool p0 = reach(a0), p1 = reach(a1);
+    const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
+    const unsigned below = (1u << lane) - 1u;
+    const int n0 = __popc(m0);
+    if (p0) enqueue(head + cnt + __popc(m0 & below), g0);
+    if (p1) enqueue(head + cnt + n0 + __popc(m1 & below), g1);
     cp_async_commit();
-    cnt += __popc(m);
-    if (before >= TV_DRAIN) {
+    const int ndrain = cnt & ~(TV_DRAIN - 1);   // whole drains among the voters queued BEFORE this iteration
+    cnt += n0 + __popc(m1);
+    if (ndrain) {
       cp_async_wait<1>();
       __syncwarp();
-      drain<EXPO, CURVES, POSW, SHELL>(ring + head, TV_DRAIN, fx, fy, fz, g, negc, lim_in, T);
-      head = (head + TV_DRAIN == TV_QCAP) ? 0 : head + TV_DRAIN;
-      cnt -= TV_DRAIN;
+      for (int d = 0; d < ndrain; d += TV_DRAIN) {
+        drain<EXPO, CURVES, POSW, SHELL>(ring + head, TV_DRAIN, fx, fy, fz, g, negc, lim_in, T);
+        head = (head + TV_DRAIN == TV_QCAP) ? 0 : head + TV_DRAIN;
+      }
+      cnt -= ndrain;
       __syncwarp();
     }
   }
-  // leftovers (<= 95), padded to an even count with a zero-weight voter
+  // leftovers, padded to an even count with a zero-weight voter
   cp_async_wait<0>();
   if (lane == 0 && (cnt & 1)) {
     int slot = head + cnt;
@@ -674,11 +695,12 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
     if (n_voters > 0) {
       DirSrc ds{direction, smoothed, ridge_sigma, eival_order, z_offset, nz_global};
       VCK(cudaMemsetAsync(sums.get() + n_scan_blocks + 1, 0, sizeof(uint32_t), ctx->stream));
-      voter_fill_kernel<<<(unsigned)n_bricks, BR3, 0, ctx->stream>>>(vs, ds, off.get(), 1.0f / info.total,
-                                                                     rec.get(),
+      voter_fill_kernel<<<(unsigned)n_bricks, BR3, 0, ctx->stream>>>(vs, off.get(), 1.0f / info.total, rec.get(),
                                                                      sums.get() + n_scan_blocks + 1);
       VCK(cudaGetLastError());
-      ctx->count_launch();
+      voter_direction_kernel<<<div_up(n_voters, 256), 256, 0, ctx->stream>>>(ds, (int)nx, (int)ny, n_voters, rec.get());
+      VCK(cudaGetLastError());
+      ctx->count_launch(2);
       VCK(cudaMemcpyAsync(&nonpos, sums.get() + n_scan_blocks + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost,
                           ctx->stream));
       VCK(cudaStreamSynchronize(ctx->stream));
