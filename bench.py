@@ -44,7 +44,7 @@ WORKLOADS = {"C4": (1024, 2048, 2048), "C2": (512, 512, 512), "dev": (256, 256, 
 CPU_SAMPLE = (128, 128, 128)
 # dram__bytes_read.sum + dram__bytes_write.sum of one tv_gather_kernel launch, from the
 # `ncu --set full` capture of the named workload (profiles/r01_tv_gather_ncu_full.csv)
-NCU_TRAFFIC_BYTES = {"dev": 27.629568e6 + 15.575552e6}
+NCU_TRAFFIC_BYTES = {"dev": 41.892864e6 + 23.390464e6}
 
 
 def parse():
