@@ -349,6 +349,18 @@ def test_membrane_device_path_identical(ctx):
     assert ctx.last_voter_count() > 0
 
 
+def test_membrane_host_path_chunked_d2h(ctx):
+    """>= 64 planes: with host arrays the voting runs in z-chunks whose results are copied back
+    behind the kernels; it must equal the single-launch device path bit for bit (70 planes:
+    a ragged last chunk)."""
+    import torch
+    vol = synth.tomogram((70, 24, 40), seed=16)
+    a = ctx.membrane(vol, 1.5, 2.6482, 1, 0.08, True, 4.3, 4, SQ2)
+    b = ctx.membrane(torch.from_numpy(vol).cuda(), 1.5, 2.6482, 1, 0.08, True, 4.3, 4, SQ2)
+    assert np.array_equal(a["out"], b["out"].cpu().numpy())
+    assert np.count_nonzero(a["out"]) > 0
+
+
 # ---- thresholds -----------------------------------------------------------------------------------------
 def test_thresholds_bit_exact(ctx, oracle, golden):
     x = golden["thr_x"]

@@ -285,8 +285,9 @@ int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, cons
     TVParams tp{p->tv_sigma, p->tv_exponent, p->tv_cutoff_ratio, 0};
     // voters' directions: the stored field if the caller asked for it, else recomputed
     // for the surviving ~5 % only
-    tv_device(ctx, nx, ny, nz, 0, nz, 0, nz, sal, thr, dir.get(), sm.get(), p->sigma, p->eival_order,
-              VISFD_SCORE_PLANAR, m.get(), m.get(), tp, tn.get(), o.get());
+    // with a host `out` the result travels back chunk by chunk behind the voting kernels
+    o.delivered = tv_device(ctx, nx, ny, nz, 0, nz, 0, nz, sal, thr, dir.get(), sm.get(), p->sigma, p->eival_order,
+                            VISFD_SCORE_PLANAR, m.get(), m.get(), tp, tn.get(), o.get(), host ? out : nullptr);
     if (hs.get()) apply_cut_device(ctx, N, hs.get(), thr);
   } else {
     apply_cut_device(ctx, N, sal, thr);

@@ -44,6 +44,7 @@ struct visfd_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;       // lazily created: D2H of finished result chunks behind the kernels
   int64_t launches = 0;
   int64_t last_voters = 0;
   bool fast_gauss = false;                  // FFMA sweeps instead of the bit-exact mul+add
@@ -127,8 +128,9 @@ struct Staged {
       VCK(cudaMemcpyAsync(dev, user, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
     }
   }
+  bool delivered = false;  // the producer already copied the result to the user's array
   void finish() {  // copy results back (outputs only)
-    if (host && dev && dir != Dir::In) {
+    if (host && dev && dir != Dir::In && !delivered) {
       StageTimer t(ctx, "d2h");
       VCK(cudaMemcpyAsync(user, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -163,6 +163,7 @@ void visfd_cuda_destroy(visfd_ctx *ctx) {
   ctx->trim();
   for (auto &kv : ctx->live_blocks) cudaFree(kv.first);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 

@@ -65,12 +65,15 @@ struct TVParams {
 // are recomputed from `smoothed` (fused pipeline: finite-difference Hessian + eigenvector
 // with ridge_sigma / eival_order).  tensor (optional): (own_z1-own_z0)*ny*nx*6.
 // score (optional): (own_z1-own_z0)*ny*nx floats = ScoreTensorPlanar/Linear of the vote
-// tensor diagonalised with eival_order.
-void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
+// tensor diagonalised with eival_order.  score_host (optional, HOST pointer of the same
+// size): the receiver planes are voted in up to 8 chunks and every finished chunk of
+// `score` is copied to score_host on a second stream while the next chunk is computed;
+// returns true if score_host has been filled that way.
+bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
                i64 own_z0, i64 own_z1, const float *saliency, float thr, const float *direction,
                const float *smoothed, float ridge_sigma, int eival_order, int score_kind,
                const float *mask_src, const float *mask_dst, const TVParams &p, float *tensor,
-               float *score);
+               float *score, float *score_host = nullptr);
 int tv_halfwidth(float sigma, float cutoff_ratio);
 
 // ---- threshold.cu -----------------------------------------------------------------

@@ -650,11 +650,11 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
 // ---------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------
-void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
+bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
                i64 own_z0, i64 own_z1, const float *saliency, float thr, const float *direction,
                const float *smoothed, float ridge_sigma, int eival_order, int score_kind,
                const float *mask_src, const float *mask_dst, const TVParams &p, float *tensor,
-               float *score) {
+               float *score, float *score_host) {
   VREQUIRE(nx > 0 && ny > 0 && nz_local > 0, "empty volume");
   VREQUIRE(own_z0 >= 0 && own_z1 <= nz_local && own_z0 <= own_z1, "receiver planes outside the slab");
   VREQUIRE(p.sigma > 0.0f, "tensor-voting sigma must be positive");
@@ -662,7 +662,7 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   const int hw = tv_halfwidth(p.sigma, p.cutoff_ratio);
   VREQUIRE(hw >= 0 && hw <= TV_MAX_REACH * BR, "tensor-voting radius too large (max 56 voxels)");
   VREQUIRE(nx <= (1 << 23) && ny <= (1 << 23) && nz_local <= (1 << 23), "slab too large");
-  if (own_z1 == own_z0) return;
+  if (own_z1 == own_z0) return false;
   DecayInfo info = decay_info(p.sigma, hw);
   VREQUIRE((int)info.shell_keep.size() <= TV_MAX_SHELL, "too many lattice points on the support shell");
 
@@ -731,16 +731,29 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   g.half_exp = 0.5f * (float)p.exponent;
   g.mask_dst = mask_dst; g.tensor = tensor; g.score = score;
   g.order = eival_order; g.score_kind = score_kind;
-  const i64 ntz = div_up(own_z1 - own_z0, BR);
-  const i64 n_tiles = (i64)g.ntx * g.nty * ntz;
-  VREQUIRE(n_tiles < 2147483647LL, "too many receiver tiles for one launch");
+  // receiver planes in chunks (multiples of the 8-plane tile): one launch each, so that a
+  // finished chunk of the result can travel to the host while the next one is computed
+  const i64 planes = own_z1 - own_z0;
+  const bool overlap_d2h = score_host && score && planes >= 8 * BR;
+  const i64 chunk_planes = overlap_d2h ? ((planes + 7) / 8 + BR - 1) / BR * BR : planes;
+  const int n_chunks = (int)((planes + chunk_planes - 1) / chunk_planes);
+  VREQUIRE((i64)g.ntx * g.nty * div_up(chunk_planes, BR) < 2147483647LL, "too many receiver tiles for one launch");
+  std::vector<cudaEvent_t> chunk_done;
+  const GatherArgs g_all = g;
   {
     StageTimer t(ctx, "tv");
-    const unsigned grid = (unsigned)n_tiles;
     // POSW: all voter weights > 0 (always true for the planar ridge score), so log2(weight)
     // rides in the decay exponent
     const size_t per_warp = (TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t) + 15) & ~(size_t)15;
     const size_t smem = (TV_THREADS / 32) * per_warp;
+    for (int c = 0; c < n_chunks; c++) {
+    g = g_all;
+    g.own_z0 = g_all.own_z0 + c * chunk_planes;
+    g.own_z1 = std::min(g_all.own_z1, g.own_z0 + chunk_planes);
+    const size_t chunk_off = (size_t)(g.own_z0 - g_all.own_z0) * (size_t)nx * (size_t)ny;
+    if (g_all.score) g.score = g_all.score + chunk_off;
+    if (g_all.tensor) g.tensor = g_all.tensor + 6 * chunk_off;
+    const unsigned grid = (unsigned)((i64)g.ntx * g.nty * div_up(g.own_z1 - g.own_z0, BR));
 #define TV_LAUNCH1(E, C, P, S)                                                                            \
     do {                                                                                                  \
       VCK(cudaFuncSetAttribute(tv_gather_kernel<E, C, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -769,10 +782,33 @@ void tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
 #undef TV_LAUNCH1
     VCK(cudaGetLastError());
     ctx->count_launch();
+    if (overlap_d2h) {
+      cudaEvent_t ev;
+      VCK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      VCK(cudaEventRecord(ev, ctx->stream));
+      chunk_done.push_back(ev);
+    }
+    }  // chunks
+  }
+  if (overlap_d2h) {
+    // all launches are queued; now the copies, each behind its chunk (with pageable host memory
+    // cudaMemcpyAsync blocks the host, which no longer delays any launch)
+    if (!ctx->copy_stream) VCK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    const size_t plane = (size_t)nx * (size_t)ny;
+    for (int c = 0; c < n_chunks; c++) {
+      const size_t off = (size_t)c * (size_t)chunk_planes * plane;
+      const size_t cnt = (size_t)std::min(chunk_planes, planes - c * chunk_planes) * plane;
+      VCK(cudaStreamWaitEvent(ctx->copy_stream, chunk_done[c], 0));
+      VCK(cudaMemcpyAsync(score_host + off, g_all.score + off, cnt * sizeof(float), cudaMemcpyDeviceToHost,
+                          ctx->copy_stream));
+    }
+    VCK(cudaStreamSynchronize(ctx->copy_stream));
+    for (cudaEvent_t ev : chunk_done) cudaEventDestroy(ev);
   }
   // the Scratch buffers are returned to the pool on scope exit; the pool is
   // stream-ordered, so the kernels above keep exclusive use until they finish.
   VCK(cudaStreamSynchronize(ctx->stream));
+  return overlap_d2h;
 }
 
 }  // namespace visfd_cuda
