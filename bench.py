@@ -32,6 +32,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version / debug chatter goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "Gvoxel/s of filter_mrc membrane+TV pipeline"
 SQ2 = float(np.float32(np.sqrt(2.0)))
@@ -302,15 +304,14 @@ def main():
 
             def e2e_step():
                 own.copy_(h_src, non_blocking=True)
-                pipe.run(own, out=d_out)
-                h_out.copy_(d_out, non_blocking=True)
+                pipe.run(own, out=d_out, out_host=h_out)   # D2H chunk by chunk behind the voting kernels
                 torch.cuda.current_stream().synchronize()
         e2e_step()
         e2e_ms = timed(e2e_step, max(1, min(args.steps, 2)))
         e2e = {"value": n_vox / (e2e_ms * 1e-3) / 1e9, "unit": "Gvoxel/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(4 * n_vox), "d2h_bytes_per_step": int(4 * n_vox),
                "call": "visfd_cuda_membrane(host pointers)" if world == 1 else
-                       "pinned host slab -> H2D -> SlabMembrane.run -> D2H, per rank"}
+                       "pinned host slab -> H2D -> SlabMembrane.run(out_host=pinned) -> chunked D2H, per rank"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------
     cpu = None

@@ -235,6 +235,16 @@ int visfd_cuda_vote_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_loca
                          int64_t vote_z0, int64_t vote_z1, const float *saliency,
                          const float *smoothed, const float *mask, float threshold,
                          const visfd_membrane_params *p, float *out, float *tensor);
+/* The same, and the result also delivered to the HOST array out_host ((own_z1-own_z0)*ny*nx
+ * floats): the receiver planes are voted in chunks and each finished chunk is copied back on
+ * a second stream while the next one is computed (the slab counterpart of what
+ * visfd_cuda_membrane does for a host `out`). */
+int visfd_cuda_vote_slab_host(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local,
+                              int64_t z_offset, int64_t nz_global, int64_t own_z0, int64_t own_z1,
+                              int64_t vote_z0, int64_t vote_z1, const float *saliency,
+                              const float *smoothed, const float *mask, float threshold,
+                              const visfd_membrane_params *p, float *out, float *tensor,
+                              float *out_host);
 
 /* ---- bookkeeping for benchmarks (no reference counterpart) ------------------------- */
 /* Enable/disable the per-stage CUDA-event timing behind visfd_cuda_stage_ms. */

@@ -448,3 +448,23 @@ def test_slab_stages_reproduce_whole_volume(ctx, world):
         res, _ = ctx.vote_slab(sal, sm, pl.slab[0], shape[0], pl.own_local, pl.vote_local, thr, p)
         out[pl.own[0]:pl.own[1]] = res.cpu().numpy()
     assert rel_err(out, whole["out"], floor_frac=1e-2) <= 1e-5
+
+
+def test_vote_slab_host_delivery(ctx):
+    """visfd_cuda_vote_slab_host: the host copy (chunked D2H behind the kernels when the slab owns
+    >= 64 planes, one plain copy otherwise) equals the device result"""
+    import torch
+    from visfd_b200.slab import make_plan
+    for shape, world in (((80, 24, 40), 1), ((60, 24, 40), 2)):
+        vol = synth.tomogram(shape, seed=21, n_shells=2)
+        sigma, ratio, tv_sigma = 1.5, 2.6482, 4.3
+        p = vb.MembraneParams(sigma, ratio, 1, 0.08, 1, tv_sigma, 4, SQ2)
+        gauss_hw = int(np.floor(np.float32(sigma) * np.float32(ratio)))
+        pl = make_plan(shape[0], world, 0, gauss_hw, vb.tv_halfwidth(tv_sigma, SQ2))
+        dvol = torch.from_numpy(vol).cuda()
+        sm, sal = ctx.ridge_saliency_slab(dvol[pl.slab[0]:pl.slab[1]].contiguous(), pl.slab[0], shape[0], sigma, ratio)
+        thr = float(np.quantile(sal.cpu().numpy(), 0.92))
+        host = np.full((pl.own[1] - pl.own[0],) + shape[1:], -1.0, np.float32)
+        res, _ = ctx.vote_slab(sal, sm, pl.slab[0], shape[0], pl.own_local, pl.vote_local, thr, p, out_host=host)
+        assert np.array_equal(host, res.cpu().numpy())
+        assert np.count_nonzero(host) > 0

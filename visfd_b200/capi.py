@@ -356,15 +356,20 @@ class Context:
         return smoothed, saliency
 
     def vote_slab(self, saliency, smoothed, z_offset, nz_global, own, vote, threshold, params, mask=None,
-                  want_tensor=False, out=None):
+                  want_tensor=False, out=None, out_host=None):
+        """out_host (optional, host array of the own planes): filled chunk by chunk behind the kernels."""
+        if out_host is not None and _is_torch(out_host):
+            assert not out_host.is_cuda
+            out_host = out_host.numpy()
         shape = tuple(saliency.shape)
         n_own = own[1] - own[0]
         res = out if out is not None else _empty(saliency, (n_own,) + shape[1:])
         tensor = _empty(saliency, (n_own,) + shape[1:] + (6,)) if want_tensor else None
-        self._ck(self.lib.visfd_cuda_vote_slab(self.h, *self._dims(shape), _i64(z_offset), _i64(nz_global),
-                                               _i64(own[0]), _i64(own[1]), _i64(vote[0]), _i64(vote[1]),
-                                               _ptr(saliency), _ptr(smoothed), _ptr(_prep(mask)), _f(threshold),
-                                               C.byref(params), _ptr(res), _ptr(tensor)))
+        self._ck(self.lib.visfd_cuda_vote_slab_host(self.h, *self._dims(shape), _i64(z_offset), _i64(nz_global),
+                                                    _i64(own[0]), _i64(own[1]), _i64(vote[0]), _i64(vote[1]),
+                                                    _ptr(saliency), _ptr(smoothed), _ptr(_prep(mask)),
+                                                    _f(threshold), C.byref(params), _ptr(res), _ptr(tensor),
+                                                    _ptr(out_host)))
         return res, tensor
 
     # ---- thresholds -----------------------------------------------------------------------------------------------

@@ -324,11 +324,12 @@ int visfd_cuda_ridge_saliency_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64
   API_END(ctx)
 }
 
-int visfd_cuda_vote_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
-                         int64_t nz_global, int64_t own_z0, int64_t own_z1, int64_t vote_z0, int64_t vote_z1,
-                         const float *saliency, const float *smoothed, const float *mask, float threshold,
-                         const visfd_membrane_params *p, float *out, float *tensor) {
+int visfd_cuda_vote_slab_host(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
+                              int64_t nz_global, int64_t own_z0, int64_t own_z1, int64_t vote_z0, int64_t vote_z1,
+                              const float *saliency, const float *smoothed, const float *mask, float threshold,
+                              const visfd_membrane_params *p, float *out, float *tensor, float *out_host) {
   API_BEGIN(ctx)
+  VREQUIRE(!out_host || !is_device_pointer(out_host), "out_host must be a host pointer");
   check_dims(nx, ny, nz_local);
   VREQUIRE(saliency && smoothed && p && out, "NULL argument");
   VREQUIRE(is_device_pointer(saliency) && is_device_pointer(smoothed) && is_device_pointer(out),
@@ -337,21 +338,35 @@ int visfd_cuda_vote_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_loca
            "plane ranges must nest: 0 <= vote_z0 <= own_z0 <= own_z1 <= vote_z1 <= nz_local");
   const size_t plane = (size_t)nx * ny;
   const size_t n_own = plane * (size_t)(own_z1 - own_z0);
+  bool delivered = false;
   if (p->tv_sigma > 0.0f) {
     // direction recompute reads smoothed planes vote_z0-1 .. vote_z1 (clamped at the global border)
     VREQUIRE((vote_z0 >= 1 || z_offset == 0) && (vote_z1 <= nz_local - 1 || z_offset + nz_local == nz_global),
              "slab lacks the 1-plane halo around the voter planes");
     TVParams tp{p->tv_sigma, p->tv_exponent, p->tv_cutoff_ratio, 0};
     const size_t o = plane * (size_t)vote_z0;
-    tv_device(ctx, nx, ny, vote_z1 - vote_z0, z_offset + vote_z0, nz_global, own_z0 - vote_z0,
+    if (tv_device(ctx, nx, ny, vote_z1 - vote_z0, z_offset + vote_z0, nz_global, own_z0 - vote_z0,
               own_z1 - vote_z0, saliency + o, threshold, nullptr, smoothed + o, p->sigma, p->eival_order,
-              VISFD_SCORE_PLANAR, mask ? mask + o : nullptr, mask ? mask + o : nullptr, tp, tensor, out);
+              VISFD_SCORE_PLANAR, mask ? mask + o : nullptr, mask ? mask + o : nullptr, tp, tensor, out, out_host))
+      delivered = true;
   } else {
     VCK(cudaMemcpyAsync(out, saliency + plane * (size_t)own_z0, n_own * sizeof(float), cudaMemcpyDeviceToDevice,
                         ctx->stream));
     apply_cut_device(ctx, n_own, out, threshold);
   }
+  if (out_host && !delivered) {
+    VCK(cudaMemcpyAsync(out_host, out, n_own * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VCK(cudaStreamSynchronize(ctx->stream));
+  }
   API_END(ctx)
+}
+
+int visfd_cuda_vote_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
+                         int64_t nz_global, int64_t own_z0, int64_t own_z1, int64_t vote_z0, int64_t vote_z1,
+                         const float *saliency, const float *smoothed, const float *mask, float threshold,
+                         const visfd_membrane_params *p, float *out, float *tensor) {
+  return visfd_cuda_vote_slab_host(ctx, nx, ny, nz_local, z_offset, nz_global, own_z0, own_z1, vote_z0, vote_z1,
+                                   saliency, smoothed, mask, threshold, p, out, tensor, nullptr);
 }
 
 // ---- threshold / mask maps --------------------------------------------------------------------------

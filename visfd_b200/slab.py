@@ -142,8 +142,10 @@ class SlabMembrane:
         self.threshold = None
         self.stage_ms = {}
 
-    def run(self, own_src, out=None, want_tensor=False):
-        """own_src: this rank's planes (device tensor).  Returns (out, tensor) for them."""
+    def run(self, own_src, out=None, want_tensor=False, out_host=None):
+        """own_src: this rank's planes (device tensor).  Returns (out, tensor) for them.
+        out_host (optional, host array/tensor of the own planes): also receives the result,
+        copied chunk by chunk behind the voting kernels."""
         p, plan, be = self.params, self.plan, self.backend
         if hasattr(be, "reset_stage_ms"):
             be.reset_stage_ms()
@@ -166,7 +168,7 @@ class SlabMembrane:
             thr = p.cut
         self.threshold = thr
         res = be.vote_slab(self.saliency, self.smoothed, plan.slab[0], self.nz, plan.own_local, plan.vote_local,
-                           thr, p, want_tensor=want_tensor, out=out)
+                           thr, p, want_tensor=want_tensor, out=out, **({"out_host": out_host} if out_host is not None else {}))
         self._grab("gauss", "ridge", "select", "compact", "tv")
         return res
 
