@@ -20,6 +20,8 @@ CPU tests (gloo, world_size 2) plug in a stand-in so that this file's plumbing -
 plan, the halo exchange, the distributed select -- is tested without a GPU.
 """
 from dataclasses import dataclass
+import os
+
 import numpy as np
 
 
@@ -124,6 +126,31 @@ def distributed_cut_threshold(backend, saliency_own, fraction, mask_own=None, di
     return backend.key_to_float(prefix)
 
 
+class _Trace:
+    """VISFD_SLAB_TRACE=1: wall-clock per phase of SlabMembrane.run (with device syncs), to stderr."""
+
+    def __init__(self, device):
+        import time
+        import torch
+        self.time, self.torch, self.device = time, torch, device
+        self.marks = []
+        if device is not None:
+            torch.cuda.synchronize(device)
+        self.t = time.perf_counter()
+
+    def mark(self, name):
+        if self.device is not None:
+            self.torch.cuda.synchronize(self.device)
+        t = self.time.perf_counter()
+        self.marks.append((name, (t - self.t) * 1e3))
+        self.t = t
+
+    def report(self, rank, stage_ms):
+        import sys
+        print("slab trace rank %d: " % rank + ", ".join("%s %.1f ms" % m for m in self.marks) +
+              " | kernels: " + ", ".join("%s %.1f" % kv for kv in stage_ms.items()), file=sys.stderr)
+
+
 class SlabMembrane:
     """HandleTV's pipeline (handlers.cpp:1618-1892) on this rank's slab."""
 
@@ -150,6 +177,7 @@ class SlabMembrane:
         if hasattr(be, "reset_stage_ms"):
             be.reset_stage_ms()
         self.stage_ms = {}
+        trace = _Trace(self.device) if os.environ.get("VISFD_SLAB_TRACE") == "1" else None
         if plan.world == 1:
             src = own_src                      # the slab IS the volume: no copy
         else:
@@ -158,8 +186,12 @@ class SlabMembrane:
                 self.slab_src = torch.empty_like(self.smoothed)
             exchange_halo(plan, own_src, self.slab_src, self.dist)
             src = self.slab_src
+        if trace:
+            trace.mark("halo")
         be.ridge_saliency_slab(src, plan.slab[0], self.nz, p.sigma, p.truncate_ratio,
                                order=p.eival_order, smoothed=self.smoothed, saliency=self.saliency)
+        if trace:
+            trace.mark("gauss+ridge")
         o0, o1 = plan.own_local
         if p.cut_is_fraction:
             thr = distributed_cut_threshold(be, self.saliency[o0:o1], p.cut, dist=self.dist, world=plan.world,
@@ -167,9 +199,14 @@ class SlabMembrane:
         else:
             thr = p.cut
         self.threshold = thr
+        if trace:
+            trace.mark("cut")
         res = be.vote_slab(self.saliency, self.smoothed, plan.slab[0], self.nz, plan.own_local, plan.vote_local,
                            thr, p, want_tensor=want_tensor, out=out, **({"out_host": out_host} if out_host is not None else {}))
         self._grab("gauss", "ridge", "select", "compact", "tv")
+        if trace:
+            trace.mark("vote")
+            trace.report(plan.rank, self.stage_ms)
         return res
 
     def _grab(self, *names):
