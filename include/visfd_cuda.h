@@ -284,6 +284,20 @@ int visfd_cuda_threshold(visfd_ctx *ctx, int64_t n_voxels, const float *in, floa
 int visfd_cuda_mean_stddev(visfd_ctx *ctx, int64_t n_voxels, const float *in,
                            const float *weights, float *mean_out, float *stddev_out);
 
+/* ---- binning (the resampling filter_mrc wraps around the path) ------ */
+/* BinArray3D<float,int>: lib/visfd/resample.hpp:53-104 (caller HandleBinning,
+ * bin/filter_mrc/handlers.cpp:2361-2425).  size_* = {nx, ny, nz}; bin size per axis =
+ * size_src / size_dst (integer division; trailing source voxels are discarded); every
+ * destination voxel is the float mean of its bin, summed in the reference's order.
+ * offset: NULL or 3 shifts in [0, bin size).  HOST or DEVICE pointers (both alike). */
+int visfd_cuda_bin3d(visfd_ctx *ctx, const int64_t size_src[3], const int64_t size_dst[3],
+                     const float *src, float *dst, const int *offset);
+/* UnbinArray3D<float,int>: lib/visfd/resample.hpp:106-166 (caller handlers.cpp:2321-2355):
+ * dst[Z][Y][X] = src[clamp((Z-oz)/bz)][clamp((Y-oy)/by)][clamp((X-ox)/bx)], bin size =
+ * size_dst / size_src. */
+int visfd_cuda_unbin3d(visfd_ctx *ctx, const int64_t size_src[3], const int64_t size_dst[3],
+                       const float *src, float *dst, const int *offset);
+
 /* ---- scale-space blob detection ----------------------------------------------------- */
 /* BlobDog<float>: lib/visfd/feature.hpp:56-427.  Results are written to caller
  * (HOST) buffers of `capacity` entries each: crds (capacity*3, voxel x,y,z),

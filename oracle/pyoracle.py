@@ -237,6 +237,27 @@ class Oracle:
         return self._fn("stddev", _f)(*self._dims(a.shape), _ptr(a), _ptr(w))
 
     # ---- blobs ---------------------------------------------------------------
+    def _resample(self, name, a, dst_shape, offset):
+        a = _f32(a)
+        out = np.empty(tuple(dst_shape), np.float32)
+        ss = (_i64 * 3)(a.shape[2], a.shape[1], a.shape[0])
+        ds = (_i64 * 3)(dst_shape[2], dst_shape[1], dst_shape[0])
+        off = None if offset is None else (_i * 3)(*[int(v) for v in offset])
+        rc = self._fn(name, _i)(ss, ds, _ptr(a), _ptr(out), off)
+        if rc:
+            raise ValueError("the reference rejects these binning arguments")
+        return out
+
+    def bin3d(self, a, bin_size=None, dst_shape=None, offset=None):
+        """BinArray3D, lib/visfd/resample.hpp:53-104"""
+        if dst_shape is None:
+            dst_shape = tuple(int(n) // int(bin_size) for n in a.shape)
+        return self._resample("bin3d", a, dst_shape, offset)
+
+    def unbin3d(self, a, dst_shape, offset=None):
+        """UnbinArray3D, lib/visfd/resample.hpp:106-166"""
+        return self._resample("unbin3d", a, dst_shape, offset)
+
     def blob_dog(self, src, sigmas, delta=0.02, truncate_ratio=2.5, mask=None,
                  minima_threshold=np.inf, maxima_threshold=-np.inf, use_threshold_ratios=True,
                  capacity=1 << 20):

@@ -324,6 +324,35 @@ float ref_stddev(int nx, int ny, int nz, const float *in, const float *w) {
   return StdDevArr(size, a.p, ww.p);
 }
 
+// lib/visfd/resample.hpp:53-166.  size_* = {nx, ny, nz} as int64 (converted to the
+// reference's int); returns 1 if the reference throws.
+int ref_bin3d(const int64_t size_src[3], const int64_t size_dst[3], const float *src, float *dst,
+              const int *offset) {
+  int ss[3] = {(int)size_src[0], (int)size_src[1], (int)size_src[2]};
+  int ds[3] = {(int)size_dst[0], (int)size_dst[1], (int)size_dst[2]};
+  View3<const float> a(src, ss[0], ss[1], ss[2]);
+  View3<float> b(dst, ds[0], ds[1], ds[2]);
+  try {
+    BinArray3D(ss, ds, a.p, b.p, offset);
+  } catch (const std::exception &) {
+    return 1;
+  }
+  return 0;
+}
+int ref_unbin3d(const int64_t size_src[3], const int64_t size_dst[3], const float *src, float *dst,
+                const int *offset) {
+  int ss[3] = {(int)size_src[0], (int)size_src[1], (int)size_src[2]};
+  int ds[3] = {(int)size_dst[0], (int)size_dst[1], (int)size_dst[2]};
+  View3<const float> a(src, ss[0], ss[1], ss[2]);
+  View3<float> b(dst, ds[0], ds[1], ds[2]);
+  try {
+    UnbinArray3D(ss, ds, a.p, b.p, offset);
+  } catch (const std::exception &) {
+    return 1;
+  }
+  return 0;
+}
+
 // lib/visfd/feature.hpp:56-427 (BlobDog).  Results are returned through
 // caller-provided buffers of `capacity` entries; returns counts via n_min/n_max
 // (clipped to capacity).  Order of the lists is thread-dependent in the

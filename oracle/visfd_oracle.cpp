@@ -815,6 +815,54 @@ float vo_stddev(i64 N, const float *in, const float *w) {
 }
 
 // ---------------------------------------------------------------------------
+// Binning: lib/visfd/resample.hpp:53-104 (BinArray3D) and :106-166 (UnbinArray3D).
+// size_* = {nx, ny, nz}; offset may be NULL.  Returns 0, or 1 for the arguments the
+// reference rejects (offset out of range, :62-70 / :128-136).
+// ---------------------------------------------------------------------------
+int vo_bin3d(const i64 size_src[3], const i64 size_dst[3], const float *src, float *dst, const int *offset) {
+  i64 b[3];
+  for (int d = 0; d < 3; d++) {
+    b[d] = size_src[d] / size_dst[d];
+    if (offset && (offset[d] >= b[d] || offset[d] < 0)) return 1;
+  }
+  for (i64 Z = 0; Z < size_dst[2]; Z++)
+    for (i64 Y = 0; Y < size_dst[1]; Y++)
+      for (i64 X = 0; X < size_dst[0]; X++) {
+        float sum = 0.0f;
+        for (i64 dz = 0; dz < b[2]; dz++)
+          for (i64 dy = 0; dy < b[1]; dy++)
+            for (i64 dx = 0; dx < b[0]; dx++) {
+              i64 ix = X * b[0] + dx, iy = Y * b[1] + dy, iz = Z * b[2] + dz;
+              if (offset) { ix += offset[0]; iy += offset[1]; iz += offset[2]; }
+              sum += src[(iz * size_src[1] + iy) * size_src[0] + ix];
+            }
+        dst[(Z * size_dst[1] + Y) * size_dst[0] + X] = sum / (float)(int)(b[0] * b[1] * b[2]);
+      }
+  return 0;
+}
+int vo_unbin3d(const i64 size_src[3], const i64 size_dst[3], const float *src, float *dst, const int *offset) {
+  i64 b[3], o[3] = {0, 0, 0};
+  for (int d = 0; d < 3; d++) {
+    b[d] = size_dst[d] / size_src[d];
+    if (offset && (offset[d] >= b[d] || offset[d] < 0)) return 1;
+    if (offset) o[d] = offset[d];
+  }
+  for (i64 Z = 0; Z < size_dst[2]; Z++)
+    for (i64 Y = 0; Y < size_dst[1]; Y++)
+      for (i64 X = 0; X < size_dst[0]; X++) {
+        i64 ix = (X - o[0]) / b[0], iy = (Y - o[1]) / b[1], iz = (Z - o[2]) / b[2];   // C division, :151-153
+        if (ix < 0) ix = 0;
+        if (iy < 0) iy = 0;
+        if (iz < 0) iz = 0;
+        if (ix >= size_src[0]) ix = size_src[0] - 1;
+        if (iy >= size_src[1]) iy = size_src[1] - 1;
+        if (iz >= size_src[2]) iz = size_src[2] - 1;
+        dst[(Z * size_dst[1] + Y) * size_dst[0] + X] = src[(iz * size_src[1] + iy) * size_src[0] + ix];
+      }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Scale-space blob detection: lib/visfd/feature.hpp:56-427 (BlobDog).
 // For scale ir: LoG image into ring slot ir%3 (:170-176); for ir>=2 every voxel
 // of scale ir-1 is tested against its 80 neighbours in (x,y,z,scale): strict

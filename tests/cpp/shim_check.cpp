@@ -17,6 +17,8 @@ float vo_membrane(int64_t, int64_t, int64_t, const float *, const float *, float
                   float *, float *, float *, float *);
 void vo_tv_dense_stick(int64_t, int64_t, int64_t, const float *, const float *, const float *, const float *, float, int,
                        float, int, float *);
+int vo_bin3d(const int64_t[3], const int64_t[3], const float *, float *, const int *);
+int vo_unbin3d(const int64_t[3], const int64_t[3], const float *, float *, const int *);
 }
 
 // pointer tables over a flat buffer; `gap` > 0 makes rows non-contiguous
@@ -175,6 +177,33 @@ int main() {
       threw = true;
     }
     check(threw, "TVDenseStick(normalize=true) is rejected, not silently ignored");
+  }
+  // BinArray3D / UnbinArray3D (resample.hpp:53-166) through pointer tables, bit-exact
+  for (int gap = 0; gap <= 3; gap += 3) {
+    const int big[3] = {23, 17, 13}, small[3] = {11, 8, 6}, off[3] = {1, 0, 0};
+    const int64_t big64[3] = {23, 17, 13}, small64[3] = {11, 8, 6};
+    Image3<float> src(23, 17, 13, gap), dst(11, 8, 6, gap), back(23, 17, 13, gap);
+    for (int z = 0; z < 13; z++)
+      for (int y = 0; y < 17; y++)
+        for (int x = 0; x < 23; x++) src.p()[z][y][x] = noise(rng);
+    std::vector<float> fsrc = src.flat(), want(11 * 8 * 6), wantb(23 * 17 * 13);
+    char label[128];
+    visfd_cuda::BinArray3D(big, small, src.p(), dst.p(), off);
+    vo_bin3d(big64, small64, fsrc.data(), want.data(), off);
+    std::snprintf(label, sizeof label, "BinArray3D bit-exact (row gap %d)", gap);
+    check(dst.flat() == want, label);
+    visfd_cuda::UnbinArray3D(small, big, dst.p(), back.p());
+    vo_unbin3d(small64, big64, want.data(), wantb.data(), nullptr);
+    std::snprintf(label, sizeof label, "UnbinArray3D bit-exact (row gap %d)", gap);
+    check(back.flat() == wantb, label);
+    bool threw = false;
+    const int bad[3] = {2, 0, 0};
+    try {
+      visfd_cuda::BinArray3D(big, small, src.p(), dst.p(), bad);
+    } catch (const std::exception &e) {
+      threw = true;
+    }
+    check(threw, "BinArray3D throws for an offset outside [0, bin size)");
   }
   std::printf("%s (%d failure%s)\n", failures ? "FAILED" : "OK", failures, failures == 1 ? "" : "s");
   return failures ? 1 : 0;

@@ -136,6 +136,15 @@ def main():
                             use_threshold_ratios=True)
     out["blob_minima_ratio"], out["blob_maxima_ratio"] = mn2, mx2
 
+    # ---- binning (lib/visfd/resample.hpp) -------------------------------------------------------------
+    bsrc = np.random.default_rng(23).standard_normal((13, 17, 22)).astype(np.float32)
+    out["bin_src"] = bsrc
+    out["bin_2"] = ref.bin3d(bsrc, bin_size=2)
+    out["bin_3"] = ref.bin3d(bsrc, bin_size=3)
+    out["bin_aniso_off"] = ref.bin3d(bsrc, dst_shape=(4, 5, 7), offset=(1, 2, 0))
+    out["unbin_2"] = ref.unbin3d(out["bin_2"], (13, 17, 22))
+    out["unbin_2_off"] = ref.unbin3d(out["bin_2"], (13, 17, 22), offset=(1, 0, 1))
+
     # ---- C1: the reference's own membrane test, run by the stock filter_mrc binary -----------------
     fm = os.path.join(ROOT, "oracle", "_ref", "filter_mrc")
     fixture = os.path.join(REFERENCE, "tests", "test_image_membrane.rec")
@@ -160,6 +169,8 @@ def main():
         sigma = np.float32(sigma / vw)
         tv_sigma = np.float32(tv_sigma / vw)
         ratio = np.float32(np.sqrt(np.float32(-2) * np.log(np.float32(0.03))))
+        assert np.array_equal(ref.bin3d(raw, bin_size=2), binned)
+        out["c1_in_raw"] = raw
         out["c1_in_binned"] = binned
         out["c1_params"] = np.array([sigma, ratio, tv_sigma, 4, np.float32(np.sqrt(2.0)), 0.05], np.float32)
         out["c1_out"] = c1

@@ -468,3 +468,53 @@ def test_vote_slab_host_delivery(ctx):
         res, _ = ctx.vote_slab(sal, sm, pl.slab[0], shape[0], pl.own_local, pl.vote_local, thr, p, out_host=host)
         assert np.array_equal(host, res.cpu().numpy())
         assert np.count_nonzero(host) > 0
+
+
+# ---- binning ------------------------------------------------------------------------
+def test_binning_bit_exact(ctx, oracle, golden):
+    """BinArray3D / UnbinArray3D (lib/visfd/resample.hpp:53-166) against the reference's vectors,
+    host and device pointers, ragged sizes, shifted windows, and the reference's argument check"""
+    import torch
+    src = golden["bin_src"]
+    assert np.array_equal(ctx.bin3d(src, bin_size=2), golden["bin_2"])
+    assert np.array_equal(ctx.bin3d(src, bin_size=3), golden["bin_3"])
+    assert np.array_equal(ctx.bin3d(src, dst_shape=(4, 5, 7), offset=(1, 2, 0)), golden["bin_aniso_off"])
+    assert np.array_equal(ctx.unbin3d(golden["bin_2"], (13, 17, 22)), golden["unbin_2"])
+    assert np.array_equal(ctx.unbin3d(golden["bin_2"], (13, 17, 22), offset=(1, 0, 1)), golden["unbin_2_off"])
+    d = ctx.bin3d(torch.from_numpy(src).cuda(), bin_size=2)
+    assert d.is_cuda and np.array_equal(d.cpu().numpy(), golden["bin_2"])
+    with pytest.raises(vb.VisfdCudaError):
+        ctx.bin3d(src, bin_size=2, offset=(2, 0, 0))
+    with pytest.raises(vb.VisfdCudaError):
+        ctx.bin3d(src, dst_shape=(14, 17, 22))
+    rng = np.random.default_rng(5)
+    big = rng.standard_normal((70, 131, 259)).astype(np.float32)   # more than one CTA in every direction
+    for b in (2, 4, 5):
+        got = ctx.bin3d(big, bin_size=b)
+        assert np.array_equal(got, oracle.bin3d(big, bin_size=b))
+        assert np.array_equal(ctx.unbin3d(got, big.shape), oracle.unbin3d(got, big.shape))
+
+
+def test_c1_from_the_raw_fixture(ctx, golden):
+    """BASELINE config 1 end to end as filter_mrc runs it: -bin 2 (BinArray3D) of the 16^3 fixture,
+    then the membrane pipeline; compared with the stock binary's output"""
+    binned = ctx.bin3d(golden["c1_in_raw"], bin_size=2)
+    assert np.array_equal(binned, golden["c1_in_binned"])
+    sigma, ratio, tv_sigma, expo, tv_ratio, frac = [float(v) for v in golden["c1_params"]]
+    c1 = ctx.membrane(binned, sigma, ratio, 1, frac, True, tv_sigma, int(expo), tv_ratio)
+    assert rel_err(c1["out"], golden["c1_out"]) <= TOL_SALIENCY
+
+
+def test_binning_properties_large(ctx):
+    """size-independent properties at a bench-like size: a constant image stays constant, binning
+    commutes with a scaling by 2, and un-binning replicates every voxel over its bin"""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn((256, 512, 512), device="cuda", generator=g)
+    c = torch.full_like(a, 1.25)
+    assert torch.all(ctx.bin3d(c, bin_size=2) == 1.25)
+    b = ctx.bin3d(a, bin_size=2)
+    assert b.shape == (128, 256, 256)
+    assert torch.equal(ctx.bin3d(a * 2.0, bin_size=2), b * 2.0)
+    u = ctx.unbin3d(b, a.shape)
+    assert torch.equal(u[::2, ::2, ::2], b) and torch.equal(u[1::2, 1::2, 1::2], b) and torch.equal(u[1::2, ::2, 1::2], b)

@@ -149,3 +149,16 @@ def test_port_matches_reference_live(oracle, ref_oracle):
     for k in ("hess_saliency", "direction", "tensor", "out"):
         eq(a[k], b[k])
     assert a["threshold"] == b["threshold"]
+
+
+def test_binning_matches_reference(golden, oracle):
+    """BinArray3D / UnbinArray3D (lib/visfd/resample.hpp:53-166): the restatement is bit-identical"""
+    src = golden["bin_src"]
+    assert np.array_equal(oracle.bin3d(src, bin_size=2), golden["bin_2"])
+    assert np.array_equal(oracle.bin3d(src, bin_size=3), golden["bin_3"])
+    assert np.array_equal(oracle.bin3d(src, dst_shape=(4, 5, 7), offset=(1, 2, 0)), golden["bin_aniso_off"])
+    assert np.array_equal(oracle.unbin3d(golden["bin_2"], (13, 17, 22)), golden["unbin_2"])
+    assert np.array_equal(oracle.unbin3d(golden["bin_2"], (13, 17, 22), offset=(1, 0, 1)), golden["unbin_2_off"])
+    assert np.array_equal(oracle.bin3d(golden["c1_in_raw"], bin_size=2), golden["c1_in_binned"])
+    with pytest.raises(ValueError):
+        oracle.bin3d(src, bin_size=2, offset=(2, 0, 0))

@@ -391,6 +391,28 @@ class Context:
         self._ck(self.lib.visfd_cuda_mean_stddev(self.h, _i64(n), _ptr(a), _ptr(weights), C.byref(m), C.byref(s)))
         return m.value, s.value
 
+    # ---- binning ---------------------------------------------------------------------------------------------------
+    def _resample(self, fn, a, dst_shape, offset):
+        a = _prep(a)
+        res = _empty(a, tuple(dst_shape))
+        ss = (_i64 * 3)(a.shape[2], a.shape[1], a.shape[0])
+        ds = (_i64 * 3)(dst_shape[2], dst_shape[1], dst_shape[0])
+        off = None if offset is None else (_i * 3)(*[int(v) for v in offset])
+        self._ck(fn(self.h, ss, ds, _ptr(a), _ptr(res), off))
+        return res
+
+    def bin3d(self, a, bin_size=None, dst_shape=None, offset=None):
+        """BinArray3D (lib/visfd/resample.hpp:53-104).  a: [nz][ny][nx]; give bin_size (HandleBinning's
+        rule: destination = source // bin_size per axis) or an explicit dst_shape (nz, ny, nx);
+        offset = (ox, oy, oz)."""
+        if dst_shape is None:
+            dst_shape = tuple(int(n) // int(bin_size) for n in a.shape)
+        return self._resample(self.lib.visfd_cuda_bin3d, a, dst_shape, offset)
+
+    def unbin3d(self, a, dst_shape, offset=None):
+        """UnbinArray3D (lib/visfd/resample.hpp:106-166): nearest-voxel expansion to dst_shape (nz, ny, nx)."""
+        return self._resample(self.lib.visfd_cuda_unbin3d, a, dst_shape, offset)
+
     # ---- blobs -----------------------------------------------------------------------------------------------------
     def blob_dog(self, src, sigmas, delta=0.02, truncate_ratio=2.5, mask=None, minima_threshold=np.inf,
                  maxima_threshold=-np.inf, use_threshold_ratios=True, capacity=1 << 20):

@@ -382,6 +382,32 @@ int visfd_cuda_threshold(visfd_ctx *ctx, int64_t n, const float *in, float *out,
   API_END(ctx)
 }
 
+int visfd_cuda_bin3d(visfd_ctx *ctx, const int64_t size_src[3], const int64_t size_dst[3], const float *src,
+                     float *dst, const int *offset) {
+  API_BEGIN(ctx)
+  VREQUIRE(size_src && size_dst && src && dst, "NULL argument");
+  const size_t ns = (size_t)size_src[0] * size_src[1] * size_src[2], nd = (size_t)size_dst[0] * size_dst[1] * size_dst[2];
+  const bool host = on_host(src);
+  Staged<float> s(ctx, src, ns, Dir::In, host);
+  Staged<float> d(ctx, dst, nd, Dir::Out, host);
+  bin3d_device(ctx, size_src, size_dst, s.get(), d.get(), offset);
+  d.finish();
+  API_END(ctx)
+}
+
+int visfd_cuda_unbin3d(visfd_ctx *ctx, const int64_t size_src[3], const int64_t size_dst[3], const float *src,
+                       float *dst, const int *offset) {
+  API_BEGIN(ctx)
+  VREQUIRE(size_src && size_dst && src && dst, "NULL argument");
+  const size_t ns = (size_t)size_src[0] * size_src[1] * size_src[2], nd = (size_t)size_dst[0] * size_dst[1] * size_dst[2];
+  const bool host = on_host(src);
+  Staged<float> s(ctx, src, ns, Dir::In, host);
+  Staged<float> d(ctx, dst, nd, Dir::Out, host);
+  unbin3d_device(ctx, size_src, size_dst, s.get(), d.get(), offset);
+  d.finish();
+  API_END(ctx)
+}
+
 int visfd_cuda_mean_stddev(visfd_ctx *ctx, int64_t n, const float *in, const float *weights, float *mean_out,
                            float *stddev_out) {
   API_BEGIN(ctx)

@@ -83,6 +83,13 @@ void threshold_device(visfd_ctx *ctx, i64 n, const float *in, float *out, int ki
 void mean_stddev_device(visfd_ctx *ctx, i64 n, const float *in, const float *w, float *mean,
                         float *stddev);
 
+// ---- resample.cu ------------------------------------------------------------------
+// BinArray3D / UnbinArray3D (lib/visfd/resample.hpp:53-166); sizes are {nx, ny, nz}.
+void bin3d_device(visfd_ctx *ctx, const i64 size_src[3], const i64 size_dst[3], const float *src, float *dst,
+                  const int *offset);
+void unbin3d_device(visfd_ctx *ctx, const i64 size_src[3], const i64 size_dst[3], const float *src, float *dst,
+                    const int *offset);
+
 // ---- blob.cu ----------------------------------------------------------------------
 struct BlobList {
   std::vector<float> crds, sigma, score;  // crds: 3 per entry (x,y,z)

@@ -305,6 +305,22 @@ inline float MembranePipeline(int const image_size[3], float const *const *const
   return thr;
 }
 
+// ---- binning (lib/visfd/resample.hpp:53-166; callers handlers.cpp:2361-2425, :2321-2355) ---------
+inline void BinArray3D(int const size_source[3], int const size_dest[3], float const *const *const *aaafSource,
+                       float ***aaafDest, int const *offset = nullptr) {
+  Dense3<float, 1> s(size_source, aaafSource, false), d(size_dest, aaafDest, true);
+  const int64_t ss[3] = {size_source[0], size_source[1], size_source[2]}, ds[3] = {size_dest[0], size_dest[1], size_dest[2]};
+  Check(visfd_cuda_bin3d(Context(), ss, ds, s.data(), d.data(), offset));
+  d.commit();
+}
+inline void UnbinArray3D(int const size_source[3], int const size_dest[3], float const *const *const *aaafSource,
+                         float ***aaafDest, int const *offset = nullptr) {
+  Dense3<float, 1> s(size_source, aaafSource, false), d(size_dest, aaafDest, true);
+  const int64_t ss[3] = {size_source[0], size_source[1], size_source[2]}, ds[3] = {size_dest[0], size_dest[1], size_dest[2]};
+  Check(visfd_cuda_unbin3d(Context(), ss, ds, s.data(), d.data(), offset));
+  d.commit();
+}
+
 // ---- thresholds (lib/threshold/threshold.hpp; bin/filter_mrc/handlers.cpp:1037-1080) ------------
 inline void ThresholdImage(int const image_size[3], float const *const *const *aaafIn, float ***aaafOut, int kind,
                            const float t[4], float outA, float outB, float const *const *const *aaafMask = nullptr,
