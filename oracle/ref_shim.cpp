@@ -26,7 +26,9 @@ using namespace std;
 
 #include <visfd.hpp>
 #include <threshold.hpp>
+#include <mrc_simple.hpp>
 using namespace visfd;
+#include "../include/visfd_mrc.h"   // only for the plain header struct the tests pass around
 
 namespace {
 
@@ -347,6 +349,62 @@ int ref_unbin3d(const int64_t size_src[3], const int64_t size_dst[3], const floa
   View3<float> b(dst, ds[0], ds[1], ds[2]);
   try {
     UnbinArray3D(ss, ds, a.p, b.p, offset);
+  } catch (const std::exception &) {
+    return 1;
+  }
+  return 0;
+}
+
+// lib/mrc_simple: MrcSimple::Read(file name, rescale=false) and MrcSimple::Write(file name),
+// the header handed over in the plain struct of include/visfd_mrc.h.
+static void header_out(const MrcHeader &m, visfd_mrc_header *h) {
+  memset(h, 0, sizeof *h);
+  for (int d = 0; d < 3; d++) {
+    h->nvoxels[d] = m.nvoxels[d]; h->nstart[d] = m.nstart[d]; h->mvoxels[d] = m.mvoxels[d];
+    h->cellA[d] = m.cellA[d]; h->cellB[d] = m.cellB[d]; h->mapCRS[d] = m.mapCRS[d]; h->origin[d] = m.origin[d];
+  }
+  h->mode = m.mode; h->dmin = m.dmin; h->dmax = m.dmax; h->dmean = m.dmean; h->ispg = m.ispg; h->nsymbt = m.nsymbt;
+  memcpy(h->extra_raw_data, m.extra_raw_data, sizeof h->extra_raw_data);
+  memcpy(h->remaining_raw_data, m.remaining_raw_data, sizeof h->remaining_raw_data);
+  h->use_signed_bytes = m.use_signed_bytes ? 1 : 0;
+}
+static void header_in(const visfd_mrc_header *h, MrcHeader &m) {
+  for (int d = 0; d < 3; d++) {
+    m.nvoxels[d] = h->nvoxels[d]; m.nstart[d] = h->nstart[d]; m.mvoxels[d] = h->mvoxels[d];
+    m.cellA[d] = h->cellA[d]; m.cellB[d] = h->cellB[d]; m.mapCRS[d] = h->mapCRS[d]; m.origin[d] = h->origin[d];
+  }
+  m.mode = h->mode; m.dmin = h->dmin; m.dmax = h->dmax; m.dmean = h->dmean; m.ispg = h->ispg; m.nsymbt = h->nsymbt;
+  memcpy(m.extra_raw_data, h->extra_raw_data, sizeof h->extra_raw_data);
+  memcpy(m.remaining_raw_data, h->remaining_raw_data, sizeof h->remaining_raw_data);
+  m.use_signed_bytes = h->use_signed_bytes != 0;
+}
+int ref_mrc_read(const char *path, visfd_mrc_header *h, float *voxels, int64_t capacity) {
+  try {
+    MrcSimple t;
+    t.Read(string(path), false);
+    header_out(t.header, h);
+    const int64_t n = (int64_t)t.header.nvoxels[0] * t.header.nvoxels[1] * t.header.nvoxels[2];
+    if (n > capacity) return 2;
+    for (int iz = 0; iz < t.header.nvoxels[2]; iz++)
+      for (int iy = 0; iy < t.header.nvoxels[1]; iy++)
+        for (int ix = 0; ix < t.header.nvoxels[0]; ix++)
+          voxels[((int64_t)iz * t.header.nvoxels[1] + iy) * t.header.nvoxels[0] + ix] = t.aaafI[iz][iy][ix];
+  } catch (const std::exception &) {
+    return 1;
+  }
+  return 0;
+}
+int ref_mrc_write(const char *path, visfd_mrc_header *h, const float *voxels) {
+  try {
+    MrcSimple t;
+    t.Resize(h->nvoxels);
+    header_in(h, t.header);
+    for (int iz = 0; iz < h->nvoxels[2]; iz++)
+      for (int iy = 0; iy < h->nvoxels[1]; iy++)
+        for (int ix = 0; ix < h->nvoxels[0]; ix++)
+          t.aaafI[iz][iy][ix] = voxels[((int64_t)iz * h->nvoxels[1] + iy) * h->nvoxels[0] + ix];
+    t.Write(string(path));
+    header_out(t.header, h);
   } catch (const std::exception &) {
     return 1;
   }

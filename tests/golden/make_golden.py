@@ -36,6 +36,26 @@ def read_mrc(path):
     return a.reshape(nz, ny, nx).astype(np.float32)
 
 
+def mrc_file_bytes(mode, nvox, data, mapcrs=(1, 2, 3), imod=None, nsymbt=0):
+    """A synthetic MRC file: every header word set to something recognisable."""
+    hdr = np.zeros(256, np.int32)
+    hdr[0:3] = nvox
+    hdr[3] = mode
+    hdr[4:7] = (1, 2, 3)
+    hdr[7:10] = (9, 9, 9)
+    hdr[10:13] = np.array([10.5, 21.25, 33.75], np.float32).view(np.int32)
+    hdr[13:16] = np.array([90, 90, 90], np.float32).view(np.int32)
+    hdr[16:19] = mapcrs
+    hdr[19:22] = np.array([-1.5, 2.5, 0.25], np.float32).view(np.int32)
+    hdr[22], hdr[23] = 1, nsymbt
+    hdr[24:49] = np.arange(25) * 7 + 3
+    hdr[52:256] = np.arange(204) * 11 + 5
+    if imod is not None:
+        hdr[38], hdr[39] = 1146047817, imod
+    hdr[49:52] = np.array([1.5, -2.5, 3.5], np.float32).view(np.int32)
+    return hdr.tobytes() + data.tobytes()
+
+
 def main():
     if not have("reference"):
         raise SystemExit("oracle/_ref/libvisfd_ref.so missing: run `make -C oracle ref` first")
@@ -144,6 +164,42 @@ def main():
     out["bin_aniso_off"] = ref.bin3d(bsrc, dst_shape=(4, 5, 7), offset=(1, 2, 0))
     out["unbin_2"] = ref.unbin3d(out["bin_2"], (13, 17, 22))
     out["unbin_2_off"] = ref.unbin3d(out["bin_2"], (13, 17, 22), offset=(1, 0, 1))
+
+    # ---- MRC files (lib/mrc_simple): small files in every mode the reference reads, what its
+    # MrcSimple::Read makes of them and the bytes its MrcSimple::Write produces ----------------------
+    import ctypes
+    from visfd_b200.mrc import MrcIO
+    ref_mrc = MrcIO(ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libvisfd_ref.so")), "ref_mrc_")
+    rng = np.random.default_rng(31)
+    nvox, N = (5, 6, 7), 5 * 6 * 7
+    mrc_cases = [
+        ("m0u.rec", 0, rng.integers(0, 256, N).astype(np.uint8), {}),                  # .rec => unsigned bytes
+        ("m0s.mrc", 0, rng.integers(0, 256, N).astype(np.uint8), {}),                  # default: signed bytes
+        ("m0imod0.mrc", 0, rng.integers(0, 256, N).astype(np.uint8), dict(imod=0)),    # IMOD flag: unsigned
+        ("m0imod1.rec", 0, rng.integers(0, 256, N).astype(np.uint8), dict(imod=1)),    # IMOD flag beats .rec
+        ("m1.mrc", 1, rng.integers(-30000, 30000, N).astype(np.int16), {}),
+        ("m6.mrc", 6, rng.integers(0, 65535, N).astype(np.uint16), {}),
+        ("m2.mrc", 2, rng.standard_normal(N).astype(np.float32), dict(nsymbt=80)),     # nsymbt is ignored
+        ("m2_213.mrc", 2, rng.standard_normal(N).astype(np.float32), dict(mapcrs=(2, 1, 3))),
+        ("m1_132.rec", 1, rng.integers(-300, 300, N).astype(np.int16), dict(mapcrs=(1, 3, 2))),
+        ("m2_321.mrc", 2, rng.standard_normal(N).astype(np.float32), dict(mapcrs=(3, 2, 1))),
+    ]
+    names = []
+    with tempfile.TemporaryDirectory() as td:
+        for name, mode, data, kw in mrc_cases:
+            raw = mrc_file_bytes(mode, nvox, data, **kw)
+            pth = os.path.join(td, name)
+            open(pth, "wb").write(raw)
+            hdr, vox = ref_mrc.read(pth)
+            outp = os.path.join(td, "out_" + name)
+            ref_mrc.write(outp, hdr, vox)
+            key = name.replace(".", "_")
+            names.append(name)
+            out["mrc_in_" + key] = np.frombuffer(raw, np.uint8)
+            out["mrc_vox_" + key] = vox
+            out["mrc_hdr_" + key] = np.frombuffer(hdr.as_bytes(), np.uint8)     # after Write: with dmin/dmax/dmean
+            out["mrc_out_" + key] = np.frombuffer(open(outp, "rb").read(), np.uint8)
+    out["mrc_names"] = np.array(names)
 
     # ---- C1: the reference's own membrane test, run by the stock filter_mrc binary -----------------
     fm = os.path.join(ROOT, "oracle", "_ref", "filter_mrc")

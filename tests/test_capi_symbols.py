@@ -11,9 +11,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "visfd_cuda.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(visfd_cuda_\w+)\s*\(", text)))
+    """every function declared in include/*.h (visfd_cuda.h: the GPU path; visfd_mrc.h: MRC file I/O)"""
+    names = set()
+    for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names.update(re.findall(r"\b(visfd_(?:cuda|mrc)_\w+)\s*\(", text))
+    return sorted(names)
 
 
 def test_header_symbols_exported():
@@ -22,12 +26,14 @@ def test_header_symbols_exported():
     names = declared_symbols()
     assert len(names) >= 30
     for n in names:
-        assert hasattr(lib, n), f"{n} declared in include/visfd_cuda.h but not exported"
+        assert hasattr(lib, n), f"{n} declared in include/*.h but not exported"
+    assert "visfd_mrc_read" in names and "visfd_cuda_bin3d" in names
 
 
 def test_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "visfd_cuda.h"\nint main(void){ visfd_membrane_params p; (void)p; return 0; }\n')
+    src.write_text('#include "visfd_cuda.h"\n#include "visfd_mrc.h"\n'
+                   'int main(void){ visfd_membrane_params p; visfd_mrc_header h; (void)p; (void)h; return 0; }\n')
     import subprocess
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
                            "-c", str(src), "-o", str(tmp_path / "t.o")])
