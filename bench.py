@@ -160,6 +160,48 @@ def workload_config(name, shape):
             "l2": "inputs (>= 0.5 GB per volume) exceed the 126 MB L2; no flush needed"}
 
 
+def gauss_c2_table(ctx, dev, hbm_peak):
+    """ApplyGauss and ApplyDog (sigma, 1.6 sigma) on a synthetic 512^3 volume for sigma 2, 4, 8
+    (half-widths 5, 10, 21), device resident, CUDA events, 5 launches after 2
+    warm-ups.  Algorithmic bytes: 24 B/voxel per Gaussian, 48 per DoG.  `exact` is the
+    default bit-identical arithmetic (un-fused multiply and add per tap), `fast` the FFMA mode."""
+    import torch
+    import visfd_b200
+    from visfd_b200 import synth
+    shape = WORKLOADS["C2"]
+    vol = synth.tomogram_torch(shape, dev, seed=1)
+    n = float(np.prod(shape))
+    rows = []
+
+    def timed_ms(fn):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 5
+
+    for mode in ("exact", "fast"):
+        ctx.set_fast_gauss(mode == "fast")
+        for sigma in (2.0, 4.0, 8.0):
+            hw = visfd_b200.gauss_halfwidth(sigma)
+            hw_dog = visfd_b200.gauss_halfwidth(1.6 * sigma)
+            ms_g = timed_ms(lambda: ctx.apply_gauss(vol, [sigma] * 3, [hw] * 3))
+            ms_d = timed_ms(lambda: ctx.apply_dog(vol, [sigma] * 3, [1.6 * sigma] * 3, [hw_dog] * 3))
+            rows.append({"mode": mode, "sigma": sigma, "halfwidth": hw, "gauss_ms": ms_g,
+                         "gauss_GBps": 24.0 * n / ms_g / 1e6, "gauss_frac_of_hbm": 24.0 * n / ms_g / 1e6 / hbm_peak,
+                         "dog_halfwidth": hw_dog, "dog_ms": ms_d, "dog_GBps": 48.0 * n / ms_d / 1e6,
+                         "dog_frac_of_hbm": 48.0 * n / ms_d / 1e6 / hbm_peak})
+    ctx.set_fast_gauss(False)
+    del vol
+    torch.cuda.empty_cache()
+    return {"shape_zyx": list(shape), "hbm_peak_GBps": hbm_peak, "rows": rows}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -282,6 +324,11 @@ def main():
              "unit": "GB/s", "algorithmic_bytes_per_voxel": 8, "kernel_ms": stage["ridge"]}
     ridge["frac"] = ridge["achieved"] / hbm_peak
 
+    # ---- BASELINE config 2: 3-D Gaussian / DoG at sigma 2, 4, 8 on 512^3 (the "Gauss HBM GB/s" half) ---
+    gauss_c2 = None
+    if rank == 0 and world == 1:
+        gauss_c2 = gauss_c2_table(ctx, dev, hbm_peak)
+
     # ---- end to end: host buffers through the public call ------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -328,7 +375,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(name, shape), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "roofline_gauss": gauss, "roofline_ridge": ridge, "cpu_baseline": cpu,
+                "roofline": roofline, "roofline_gauss": gauss, "roofline_ridge": ridge, "gauss_c2": gauss_c2,
+                "cpu_baseline": cpu,
                 "stage_ms_rank0_last_step": stage, "halo_planes": pipe.plan.halo if world > 1 else 0}
         print(json.dumps(line))
     if world > 1:
