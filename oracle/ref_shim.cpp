@@ -355,6 +355,43 @@ int ref_unbin3d(const int64_t size_src[3], const int64_t size_dst[3], const floa
   return 0;
 }
 
+// Blob list post-processing (lib/visfd/feature.hpp:521-616, :723-913, :926-969), in place on
+// flat arrays; returns the new length.
+namespace {
+struct RefList {
+  vector<array<float, 3> > crds;
+  vector<float> diam, score;
+  RefList(int64_t n, const float *c, const float *d, const float *s) : crds(n), diam(d, d + n), score(s, s + n) {
+    for (int64_t i = 0; i < n; i++) crds[i] = {c[3 * i], c[3 * i + 1], c[3 * i + 2]};
+  }
+  int64_t store(float *c, float *d, float *s) {
+    for (size_t i = 0; i < crds.size(); i++) {
+      c[3 * i] = crds[i][0]; c[3 * i + 1] = crds[i][1]; c[3 * i + 2] = crds[i][2];
+      d[i] = diam[i]; s[i] = score[i];
+    }
+    return (int64_t)crds.size();
+  }
+};
+}
+int64_t ref_blobs_sort(int64_t n, float *c, float *d, float *s, int criteria, int ascending) {
+  RefList l(n, c, d, s);
+  SortBlobs(l.crds, l.diam, l.score, (SortCriteria)criteria, ascending != 0);
+  return l.store(c, d, s);
+}
+int64_t ref_blobs_discard_masked(int64_t n, float *c, float *d, float *s, const float *mask, int64_t nx, int64_t ny,
+                                 int64_t nz) {
+  RefList l(n, c, d, s);
+  View3<const float> m(mask, (int)nx, (int)ny, (int)nz);
+  DiscardMaskedBlobs(l.crds, l.diam, l.score, m.p);
+  return l.store(c, d, s);
+}
+int64_t ref_blobs_discard_overlapping(int64_t n, float *c, float *d, float *s, float sep, float large, float small_,
+                                      int criteria) {
+  RefList l(n, c, d, s);
+  DiscardOverlappingBlobs(l.crds, l.diam, l.score, sep, large, small_, (SortCriteria)criteria);
+  return l.store(c, d, s);
+}
+
 // lib/mrc_simple: MrcSimple::Read(file name, rescale=false) and MrcSimple::Write(file name),
 // the header handed over in the plain struct of include/visfd_mrc.h.
 static void header_out(const MrcHeader &m, visfd_mrc_header *h) {

@@ -237,6 +237,82 @@ def main():
         assert np.array_equal(chk["out"], c1), "C1: library replay differs from filter_mrc output"
         print("C1: sum=%.6e max=%.6e nonzero=%d" % (c1.sum(dtype=np.float64), c1.max(), (c1 != 0).sum()))
 
+    # ---- the reference's own blob test (tests/test_blob_detection.sh:21): `-blob minima f 160 280 1.01`
+    # with -w 19.6 and a mask, run by the stock binary; the library replay with the parameters
+    # filter_mrc derives (settings.cpp:1702-1743, filter_mrc.cpp:330-333, feature.hpp:469-471) ------------
+    bfix = os.path.join(REFERENCE, "tests", "test_blob_detect.rec")
+    bmask = os.path.join(REFERENCE, "tests", "test_blob_detect_mask.rec")
+    if os.path.exists(fm) and os.path.exists(bfix):
+        img, msk = read_mrc(bfix), read_mrc(bmask)
+        with tempfile.TemporaryDirectory() as td:
+            lst = os.path.join(td, "blobs.txt")
+            subprocess.run([fm, "-w", "19.6", "-mask", bmask, "-in", bfix, "-blob", "minima", lst, "160.0", "280.0",
+                            "1.01"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            cli = np.loadtxt(lst, ndmin=2)
+        wmin, wmax, growth = np.float32(160.0), np.float32(280.0), np.float32(1.01)
+        nsc = 1 + int(np.ceil(np.log(np.float64(wmax / wmin)) / np.log(np.float64(growth))))
+        growth = np.float32(np.power(np.float64(wmax / wmin), 1.0 / nsc))
+        diam = [np.float32(wmin)]
+        for _ in range(1, nsc):
+            diam.append(np.float32(diam[-1] * growth))
+        vw = np.float32(19.6)
+        diam = np.array([np.float32(d / vw) for d in diam], np.float32)
+        sig = np.array([np.float32(np.float64(d) / (2.0 * np.sqrt(3.0))) for d in diam], np.float32)
+        ratio_b = float(np.float32(np.sqrt(-2 * np.log(np.float32(0.03)))))
+        mn_b, _ = ref.blob_dog(img, sig, 0.02, ratio_b, mask=msk, minima_threshold=0.0, maxima_threshold=-np.inf,
+                               use_threshold_ratios=False)
+        # the CLI prints x y z diameter score in physical units with 6 significant digits, best score first
+        order = np.argsort(mn_b[:, 4], kind="stable")
+        phys = np.stack([mn_b[order, 0] * vw, mn_b[order, 1] * vw, mn_b[order, 2] * vw,
+                         np.float32(mn_b[order, 3] * np.float32(2.0 * np.sqrt(3.0))) * vw, mn_b[order, 4]], axis=1)
+        assert cli.shape == phys.shape, (cli.shape, phys.shape)
+        assert np.allclose(np.sort(cli, axis=0), np.sort(phys, axis=0), rtol=2e-5), "blob fixture: replay differs from filter_mrc"
+        out["blobfix_img"], out["blobfix_mask"], out["blobfix_sigmas"] = img, msk, sig
+        out["blobfix_ratio"] = np.float32(ratio_b)
+        out["blobfix_minima"] = mn_b
+        out["blobfix_cli"] = cli
+        print("blob fixture: %d scales, %d minima" % (nsc, len(mn_b)))
+
+        # ---- ... and its non-max suppression step (tests/test_blob_detection.sh:25): `-discard-blobs
+        # in out -blob-separation 1.1 -minima-threshold -90`; known answer: 2 blobs.
+        # Replay of HandleBlobsNonmaxSuppression (handlers.cpp:428-640) with the reference's functions.
+        from visfd_b200.blobs import BlobLists, SORT_DECREASING_MAGNITUDE
+        rb = BlobLists(ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libvisfd_ref.so")), "ref_blobs_")
+        with tempfile.TemporaryDirectory() as td:
+            lst, lst2 = os.path.join(td, "blobs.txt"), os.path.join(td, "nms.txt")
+            subprocess.run([fm, "-w", "19.6", "-mask", bmask, "-in", bfix, "-blob", "minima", lst, "160.0", "280.0",
+                            "1.01"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            subprocess.run([fm, "-w", "19.6", "-mask", bmask, "-in", bfix, "-discard-blobs", lst, lst2,
+                            "-blob-separation", "1.1", "-minima-threshold", "-90"], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            txt_in = np.loadtxt(lst, ndmin=2).astype(np.float32)
+            cli2 = np.loadtxt(lst2, ndmin=2)
+        # what the CLI reads back from its own text file (6 significant digits), in voxels
+        nms_in = txt_in.copy()
+        nms_in[:, :3] = np.floor(txt_in[:, :3] / vw + np.float32(0.5))
+        nms_in[:, 3] = txt_in[:, 3] / vw
+        kept = nms_in[(nms_in[:, 4] >= -np.inf) & (nms_in[:, 4] <= np.float32(-90.0))]
+        kept = rb.discard_masked(kept, msk)
+        nms_out = rb.discard_overlapping(kept, 1.1, np.inf, np.inf, SORT_DECREASING_MAGNITUDE)
+        phys2 = nms_out.astype(np.float64) * np.array([vw, vw, vw, vw, 1.0])
+        assert cli2.shape == phys2.shape == (2, 5), (cli2.shape, phys2.shape)
+        assert np.allclose(cli2, phys2, rtol=2e-5), "blob NMS: replay differs from filter_mrc"
+        out["blobnms_in"], out["blobnms_out"], out["blobnms_cli"] = nms_in, nms_out, cli2
+        # a larger synthetic list for the list functions on their own
+        g = np.random.default_rng(77)
+        big = np.stack([g.uniform(0, 200, 600), g.uniform(0, 180, 600), g.uniform(0, 90, 600),
+                        g.uniform(4, 30, 600), g.standard_normal(600) * 50], axis=1).astype(np.float32)
+        big[::50, 4] = big[1::50, 4][:len(big[::50])]          # some tied scores
+        out["bloblist_in"] = big
+        out["bloblist_sorted_mag"] = rb.sort(big, SORT_DECREASING_MAGNITUDE, False)
+        out["bloblist_sorted_inc"] = rb.sort(big, 2, True)
+        out["bloblist_nms_sep"] = rb.discard_overlapping(big, 1.0)
+        out["bloblist_nms_vol"] = rb.discard_overlapping(big, 0.0, 0.3, 0.6)
+        out["bloblist_nms_inc"] = rb.discard_overlapping(big, 0.8, np.inf, np.inf, 2)
+        print("blob NMS: %d -> %d (CLI %d); synthetic 600 -> %d / %d / %d" % (
+            len(nms_in), len(nms_out), len(cli2), len(out["bloblist_nms_sep"]), len(out["bloblist_nms_vol"]),
+            len(out["bloblist_nms_inc"])))
+
     path = os.path.join(HERE, "reference_vectors.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "%.1f KiB" % (os.path.getsize(path) / 1024), len(out), "arrays")

@@ -16,7 +16,7 @@ def declared_symbols():
     for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
         text = open(os.path.join(ROOT, "include", header)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-        names.update(re.findall(r"\b(visfd_(?:cuda|mrc)_\w+)\s*\(", text))
+        names.update(re.findall(r"\b(visfd_(?:cuda|mrc|blobs)_\w+)\s*\(", text))
     return sorted(names)
 
 
@@ -27,12 +27,12 @@ def test_header_symbols_exported():
     assert len(names) >= 30
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/*.h but not exported"
-    assert "visfd_mrc_read" in names and "visfd_cuda_bin3d" in names
+    assert "visfd_mrc_read" in names and "visfd_cuda_bin3d" in names and "visfd_blobs_discard_overlapping" in names
 
 
 def test_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "visfd_cuda.h"\n#include "visfd_mrc.h"\n'
+    src.write_text('#include "visfd_cuda.h"\n#include "visfd_mrc.h"\n#include "visfd_blobs.h"\n'
                    'int main(void){ visfd_membrane_params p; visfd_mrc_header h; (void)p; (void)h; return 0; }\n')
     import subprocess
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),

@@ -518,3 +518,13 @@ def test_binning_properties_large(ctx):
     assert torch.equal(ctx.bin3d(a * 2.0, bin_size=2), b * 2.0)
     u = ctx.unbin3d(b, a.shape)
     assert torch.equal(u[::2, ::2, ::2], b) and torch.equal(u[1::2, 1::2, 1::2], b) and torch.equal(u[1::2, ::2, 1::2], b)
+
+
+def test_reference_blob_fixture_gpu(ctx, golden):
+    """the reference's own blob fixture (tests/test_blob_detection.sh:21; 58 scales, masked): the
+    11 minima the stock binary finds, position / scale / score bit for bit"""
+    mn, _ = ctx.blob_dog(golden["blobfix_img"], golden["blobfix_sigmas"], 0.02, float(golden["blobfix_ratio"]),
+                         mask=golden["blobfix_mask"], minima_threshold=0.0, maxima_threshold=-np.inf,
+                         use_threshold_ratios=False)
+    assert len(mn) == 11
+    assert np.array_equal(sort_blobs(mn), sort_blobs(golden["blobfix_minima"]))

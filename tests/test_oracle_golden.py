@@ -162,3 +162,20 @@ def test_binning_matches_reference(golden, oracle):
     assert np.array_equal(oracle.bin3d(golden["c1_in_raw"], bin_size=2), golden["c1_in_binned"])
     with pytest.raises(ValueError):
         oracle.bin3d(src, bin_size=2, offset=(2, 0, 0))
+
+
+def test_reference_blob_fixture(oracle, golden):
+    """the reference's own blob test (tests/test_blob_detection.sh:21): 58 scales, 11 minima
+    (SURVEY.md 8c), list produced by the stock filter_mrc binary"""
+    if "blobfix_minima" not in golden.files:
+        pytest.skip("blob fixture not generated")
+    mn, _ = oracle.blob_dog(golden["blobfix_img"], golden["blobfix_sigmas"], 0.02, float(golden["blobfix_ratio"]),
+                            mask=golden["blobfix_mask"], minima_threshold=0.0, maxima_threshold=-np.inf,
+                            use_threshold_ratios=False)
+    assert len(golden["blobfix_sigmas"]) == 58 and len(mn) == 11
+    eq(sort_blobs(mn), sort_blobs(golden["blobfix_minima"]))
+    # ... and the two blobs the reference's test expects after non-max suppression are among them
+    # (known answers of SURVEY 8c: `235.2 392 313.6 177.915 -140.018`, `254.8 98 274.4 177.915 -109.148`)
+    cli = golden["blobfix_cli"]
+    for want in ((235.2, 392.0, 313.6, 177.915, -140.018), (254.8, 98.0, 274.4, 177.915, -109.148)):
+        assert np.any(np.all(np.isclose(cli, want, rtol=1e-5), axis=1)), want
