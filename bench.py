@@ -32,8 +32,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's version / debug chatter goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version
+# banner on rank 0), so file descriptor 1 is pointed at stderr for the whole run and the result
+# goes out through a private duplicate of the original stdout.
+RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 METRIC = "Gvoxel/s of filter_mrc membrane+TV pipeline"
 SQ2 = float(np.float32(np.sqrt(2.0)))
@@ -42,7 +45,7 @@ SIGMA = float(np.float32(np.float32(5.196) / np.sqrt(3.0)))
 TV_SIGMA = float(np.float32(np.float32(4.733) * np.float32(SIGMA)))
 RATIO = float(np.float32(np.sqrt(np.float32(-2) * np.log(np.float32(0.03)))))
 TV_BEST = 0.05
-WORKLOADS = {"C4": (1024, 2048, 2048), "C2": (512, 512, 512), "dev": (256, 256, 256)}
+WORKLOADS = {"C4": (1024, 2048, 2048), "C5": (1024, 4096, 4096), "C2": (512, 512, 512), "dev": (256, 256, 256)}
 CPU_SAMPLE = (128, 128, 128)
 # dram__bytes_read.sum + dram__bytes_write.sum of one tv_gather_kernel launch, from the
 # `ncu --set full` capture of the named workload (profiles/r01_tv_gather_ncu_full.csv)
@@ -148,7 +151,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": val, "unit": "Gvoxel/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     return 0
 
 
@@ -378,7 +381,7 @@ def main():
                 "roofline": roofline, "roofline_gauss": gauss, "roofline_ridge": ridge, "gauss_c2": gauss_c2,
                 "cpu_baseline": cpu,
                 "stage_ms_rank0_last_step": stage, "halo_planes": pipe.plan.halo if world > 1 else 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
