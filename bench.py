@@ -49,7 +49,9 @@ WORKLOADS = {"C4": (1024, 2048, 2048), "C5": (1024, 4096, 4096), "C2": (512, 512
 CPU_SAMPLE = (128, 128, 128)
 # dram__bytes_read.sum + dram__bytes_write.sum of one tv_gather_kernel launch, from the
 # `ncu --set full` capture of the named workload (profiles/r01_tv_gather_ncu_full.csv)
-NCU_TRAFFIC_BYTES = {"dev": 41.892864e6 + 23.390464e6}
+# ("C4": a metrics-only ncu pass of `bench.py --steps 1 --warmup 0`: the 10.3 GB voter list is
+# re-read once per layer of receiver tiles it serves; 10.7 GB/s, nowhere near the HBM roofline)
+NCU_TRAFFIC_BYTES = {"dev": 41.892864e6 + 23.390464e6, "C4": 72.06e9 + 17.45e9}
 
 
 def parse():
