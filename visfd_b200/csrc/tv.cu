@@ -564,7 +564,6 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
     while (e >= row_pref[cur_row + 1]) cur_row++;
     return row_start[cur_row] + (e - row_pref[cur_row]);
   };
-  const float4 nowhere = make_float4(-1.0e9f, -1.0e9f, -1.0e9f, 0.0f);
   auto reach = [&](const float4 &a) -> bool {
     // exact distance from the voter (a holds the NEGATED position) to the patch box
     const float gx = fmaxf(fabsf(a.x + pcx) - 1.5f, 0.0f);
@@ -581,18 +580,25 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
     cp_async16(&dst->c, &src->c);
   };
   int head = 0, cnt = 0;
+  // candidate e of the stream, clamped to the last one so that every lane always loads (an
+  // unconditional load keeps the prefetch out of the way of the registers in use; lanes past
+  // the end are masked when their candidate is tested)
+  auto fetch = [&](uint32_t e, uint32_t &gi, float4 &a) {
+    gi = locate(min(e, total - 1));
+    a = __ldg(&g.rec[gi].a);
+  };
   uint32_t ng0 = 0, ng1 = 0;
-  float4 na0 = nowhere, na1 = nowhere;
-  if (lane < total) { ng0 = locate(lane); na0 = __ldg(&g.rec[ng0].a); }
-  if (32 + lane < total) { ng1 = locate(32 + lane); na1 = __ldg(&g.rec[ng1].a); }
+  float4 na0 = make_float4(0.f, 0.f, 0.f, 0.f), na1 = na0;
+  if (total > 0) {
+    fetch(lane, ng0, na0);
+    fetch(32 + lane, ng1, na1);
+  }
   for (uint32_t base = 0; base < total; base += 64) {
     const float4 a0 = na0, a1 = na1;
     const uint32_t g0 = ng0, g1 = ng1;
-    na0 = nowhere;
-    na1 = nowhere;
-    if (base + 64 + lane < total) { ng0 = locate(base + 64 + lane); na0 = __ldg(&g.rec[ng0].a); }
-    if (base + 96 + lane < total) { ng1 = locate(base + 96 + lane); na1 = __ldg(&g.rec[ng1].a); }
-    const bool p0 = reach(a0), p1 = reach(a1);
+    fetch(base + 64 + lane, ng0, na0);
+    fetch(base + 96 + lane, ng1, na1);
+    const bool p0 = base + lane < total && reach(a0), p1 = base + 32 + lane < total && reach(a1);
     const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
     const unsigned below = (1u << lane) - 1u;
     const int n0 = __popc(m0);
