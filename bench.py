@@ -45,13 +45,14 @@ SIGMA = float(np.float32(np.float32(5.196) / np.sqrt(3.0)))
 TV_SIGMA = float(np.float32(np.float32(4.733) * np.float32(SIGMA)))
 RATIO = float(np.float32(np.sqrt(np.float32(-2) * np.log(np.float32(0.03)))))
 TV_BEST = 0.05
-WORKLOADS = {"C4": (1024, 2048, 2048), "C5": (1024, 4096, 4096), "C2": (512, 512, 512), "dev": (256, 256, 256)}
+WORKLOADS = {"C4": (1024, 2048, 2048), "C5": (1024, 4096, 4096), "C2": (512, 512, 512), "C3": (512, 1024, 1024),
+             "dev": (256, 256, 256)}
 CPU_SAMPLE = (128, 128, 128)
 # dram__bytes_read.sum + dram__bytes_write.sum of one tv_gather_kernel launch, from the
 # `ncu --set full` capture of the named workload (profiles/r01_tv_gather_ncu_full.csv)
 # ("C4": a metrics-only ncu pass of `bench.py --steps 1 --warmup 0`: the 10.3 GB voter list is
 # re-read once per layer of receiver tiles it serves; 10.7 GB/s, nowhere near the HBM roofline)
-NCU_TRAFFIC_BYTES = {"dev": 41.892864e6 + 23.390464e6, "C4": 72.06e9 + 17.45e9}
+NCU_TRAFFIC_BYTES = {"dev": 41.19e6 + 24.87e6, "C4": 72.06e9 + 17.45e9}
 
 
 def parse():
@@ -207,6 +208,56 @@ def gauss_c2_table(ctx, dev, hbm_peak):
     return {"shape_zyx": list(shape), "hbm_peak_GBps": hbm_peak, "rows": rows}
 
 
+def blob_c3_row(ctx, dev, hbm_peak):
+    """BlobDog on BASELINE config 3: 1024x1024x512, `-blob-s minima 2 8 1.14` => 12 scales
+    sigma_n = 2 * 4^(n/12), each one ApplyLog with delta 0.02 and the shared half-width
+    floor(2.6482 * 1.01 sigma), extremum scan over scales 1..10.  Device
+    resident input with 64 dark blobs stamped in, one warm-up, two timed calls, CUDA events around the
+    whole call (the candidate lists come back to the host inside it).  Algorithmic bytes: 60 B per
+    voxel per scale."""
+    import torch
+    from visfd_b200 import synth
+    shape = WORKLOADS["C3"]
+    nz, ny, nx = shape
+    vol = synth.tomogram_torch(shape, dev, seed=2, n_shells=0)
+    rng = np.random.default_rng(3)
+    for _ in range(64):
+        bs = rng.uniform(3.0, 6.0)
+        c = [rng.uniform(24, d - 24) for d in shape]
+        lo = [int(ci - 4 * bs) for ci in c]
+        hi = [int(ci + 4 * bs) + 1 for ci in c]
+        ax = [torch.arange(a, b, dtype=torch.float32, device=dev) - ci for a, b, ci in zip(lo, hi, c)]
+        r2 = ax[0][:, None, None] ** 2 + ax[1][None, :, None] ** 2 + ax[2][None, None, :] ** 2
+        vol[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] -= 4.0 * torch.exp(-0.5 * r2 / (bs * bs))
+    n_scales = 12
+    sigmas = 2.0 * 4.0 ** (np.arange(n_scales) / n_scales)
+    ratio = float(np.sqrt(-2.0 * np.log(0.03)))
+
+    def call():
+        # `-blob-s minima` defaults (bin/filter_mrc/settings.cpp:1674-1678, :121-123): every minimum with a
+        # negative score, absolute thresholds
+        return ctx.blob_dog(vol, sigmas, delta=0.02, truncate_ratio=ratio, minima_threshold=0.0,
+                            maxima_threshold=-np.inf, use_threshold_ratios=False, capacity=1 << 24)
+
+    minima, maxima = call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(2):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    n = float(nz) * ny * nx
+    gbps = 60.0 * n * n_scales / ms / 1e6
+    del vol
+    torch.cuda.empty_cache()
+    return {"shape_zyx": list(shape), "scales": n_scales, "sigma_first_last": [float(sigmas[0]), float(sigmas[-1])],
+            "ms": ms, "Gvoxel_scales_per_s": n * n_scales / ms / 1e6, "algorithmic_bytes_per_voxel_per_scale": 60,
+            "GBps": gbps, "frac_of_hbm": gbps / hbm_peak, "minima": int(len(minima)), "maxima": int(len(maxima)),
+            "thresholds": "minima < 0, absolute (the -blob-s minima defaults)"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -330,9 +381,10 @@ def main():
     ridge["frac"] = ridge["achieved"] / hbm_peak
 
     # ---- BASELINE config 2: 3-D Gaussian / DoG at sigma 2, 4, 8 on 512^3 (the "Gauss HBM GB/s" half) ---
-    gauss_c2 = None
+    gauss_c2 = blob_c3 = None
     if rank == 0 and world == 1:
         gauss_c2 = gauss_c2_table(ctx, dev, hbm_peak)
+        blob_c3 = blob_c3_row(ctx, dev, hbm_peak)
 
     # ---- end to end: host buffers through the public call ------------------------------------------
     e2e = None
@@ -380,7 +432,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(name, shape), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "roofline_gauss": gauss, "roofline_ridge": ridge, "gauss_c2": gauss_c2,
+                "roofline": roofline, "roofline_gauss": gauss, "roofline_ridge": ridge, "gauss_c2": gauss_c2, "blob_c3": blob_c3,
                 "cpu_baseline": cpu,
                 "stage_ms_rank0_last_step": stage, "halo_planes": pipe.plan.halo if world > 1 else 0}
         print(json.dumps(line), file=RESULT_OUT, flush=True)

@@ -298,6 +298,27 @@ int visfd_cuda_bin3d(visfd_ctx *ctx, const int64_t size_src[3], const int64_t si
 int visfd_cuda_unbin3d(visfd_ctx *ctx, const int64_t size_src[3], const int64_t size_dst[3],
                        const float *src, float *dst, const int *offset);
 
+/* ---- mask rasterisation ------------------------------------------- */
+/* One primitive of the list DrawRegions paints: mirrors visfd::SimpleRegion<float>
+ * (lib/visfd/draw.hpp:41-87).  RECT: p = {xmin, xmax, ymin, ymax, zmin, zmax};
+ * SPHERE: p = {x0, y0, z0, r, -, -}; all in voxels (the caller has already divided
+ * by the voxel width, bin/filter_mrc/filter_mrc.cpp:225-270). */
+enum { VISFD_REGION_RECT = 0, VISFD_REGION_SPHERE = 1 };
+typedef struct visfd_region {
+  int32_t type;
+  float p[6];
+  float value;
+} visfd_region;
+/* DrawRegions<float>: lib/visfd/draw.hpp:90-237 (caller filter_mrc.cpp:280-284, which passes
+ * no mask and negative_means_subtract = true).  image: nz*ny*nx floats, updated IN PLACE
+ * (HOST or DEVICE pointer, mask alike); regions: HOST array.  Regions are applied in list
+ * order; voxels where mask == 0 are never touched; with negative_means_subtract a region of
+ * negative value clears the positive voxels it covers, and an all-zero image whose FIRST
+ * region is negative starts from ones (draw.hpp:98-134). */
+int visfd_cuda_draw_regions(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, float *image,
+                            const float *mask, const visfd_region *regions, int n_regions,
+                            int negative_means_subtract);
+
 /* ---- scale-space blob detection ----------------------------------------------------- */
 /* BlobDog<float>: lib/visfd/feature.hpp:56-427.  Results are written to caller
  * (HOST) buffers of `capacity` entries each: crds (capacity*3, voxel x,y,z),

@@ -42,6 +42,23 @@ def _f32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
 
 
+
+REGION_DTYPE = np.dtype([("type", np.int32), ("p", np.float32, 6), ("value", np.float32)])
+
+
+def pack_regions(regions):
+    """List of ("rect", xmin, xmax, ymin, ymax, zmin, zmax, value) / ("sphere", x0, y0, z0, r, value)
+    -> the 32-byte records both libraries take (mirrors visfd::SimpleRegion<float>, draw.hpp:41-87)."""
+    rec = np.zeros(len(regions), REGION_DTYPE)
+    for i, r in enumerate(regions):
+        if r[0] == "sphere":
+            rec[i] = (1, tuple(r[1:5]) + (0.0, 0.0), r[5])
+        elif r[0] == "rect":
+            rec[i] = (0, tuple(r[1:7]), r[7])
+        else:
+            raise ValueError("unknown region kind %r" % (r[0],))
+    return rec
+
 class Oracle:
     def __init__(self, kind="port"):
         assert kind in ("port", "reference")
@@ -257,6 +274,17 @@ class Oracle:
     def unbin3d(self, a, dst_shape, offset=None):
         """UnbinArray3D, lib/visfd/resample.hpp:106-166"""
         return self._resample("unbin3d", a, dst_shape, offset)
+
+    def draw_regions(self, image, regions, mask=None, negative_means_subtract=False):
+        """DrawRegions, lib/visfd/draw.hpp:90-237.  regions: ("rect", xmin, xmax, ymin, ymax, zmin,
+        zmax, value) or ("sphere", x0, y0, z0, r, value) in voxels.  Returns the painted copy."""
+        img = np.array(image, np.float32, order="C", copy=True)
+        mask = _f32(mask)
+        rec = pack_regions(regions)
+        nz, ny, nx = img.shape
+        self._fn("draw_regions", _i)(_i(nx), _i(ny), _i(nz), _ptr(img), _ptr(mask), _ptr(rec), _i(len(rec)),
+                                     _i(int(negative_means_subtract)))
+        return img
 
     def blob_dog(self, src, sigmas, delta=0.02, truncate_ratio=2.5, mask=None,
                  minima_threshold=np.inf, maxima_threshold=-np.inf, use_threshold_ratios=True,

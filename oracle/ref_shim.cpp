@@ -355,6 +355,37 @@ int ref_unbin3d(const int64_t size_src[3], const int64_t size_dst[3], const floa
   return 0;
 }
 
+// lib/visfd/draw.hpp:90-237.  regions: n records of {int32 type (0 rect, 1 sphere), float p[6],
+// float value}; rect p = xmin,xmax,ymin,ymax,zmin,zmax; sphere p = x0,y0,z0,r.
+struct RegionRecord { int32_t type; float p[6]; float value; };
+int ref_draw_regions(int nx, int ny, int nz, float *image, const float *mask, const RegionRecord *regions, int n,
+                     int negative_means_subtract) {
+  int size[3] = {nx, ny, nz};
+  View3<float> img(image, nx, ny, nz);
+  View3<const float> m(mask, nx, ny, nz);
+  vector<SimpleRegion<float> > v((size_t)n);
+  for (int i = 0; i < n; i++) {
+    v[i].value = regions[i].value;
+    if (regions[i].type == 1) {
+      v[i].type = SimpleRegion<float>::SPHERE;
+      v[i].data.sphere.x0 = regions[i].p[0];
+      v[i].data.sphere.y0 = regions[i].p[1];
+      v[i].data.sphere.z0 = regions[i].p[2];
+      v[i].data.sphere.r = regions[i].p[3];
+    } else {
+      v[i].type = SimpleRegion<float>::RECT;
+      v[i].data.rect.xmin = regions[i].p[0];
+      v[i].data.rect.xmax = regions[i].p[1];
+      v[i].data.rect.ymin = regions[i].p[2];
+      v[i].data.rect.ymax = regions[i].p[3];
+      v[i].data.rect.zmin = regions[i].p[4];
+      v[i].data.rect.zmax = regions[i].p[5];
+    }
+  }
+  DrawRegions(size, img.p, m.p, v, negative_means_subtract != 0);
+  return 0;
+}
+
 // Blob list post-processing (lib/visfd/feature.hpp:521-616, :723-913, :926-969), in place on
 // flat arrays; returns the new length.
 namespace {

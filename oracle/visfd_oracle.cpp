@@ -863,6 +863,75 @@ int vo_unbin3d(const i64 size_src[3], const i64 size_dst[3], const float *src, f
 }
 
 // ---------------------------------------------------------------------------
+// Mask rasterisation: lib/visfd/draw.hpp:90-237 (DrawRegions).  Regions are painted in list
+// order; a region of negative value clears positive voxels when negative_means_subtract is
+// set (:162-166, :203-207), otherwise its value is stored (:168-170).  An all-zero image
+// whose first region is negative is first filled with ones (:98-134).  Masked voxels
+// (mask == 0) are skipped everywhere.
+//   sphere (:139-172): Ri = ceil(R - 0.5); centre = floor(c + 0.5); for |jz|,|jy| <= Ri:
+//                      descr = R*R - (jy*jy + jz*jz) in float, skipped if < 0;
+//                      |jx| <= floor(sqrt(descr))
+//   box    (:176-211): corners floor(v + 0.5) kept as floats, clipped to the image
+// ---------------------------------------------------------------------------
+struct vo_region { int32_t type; float p[6]; float value; };
+static void vo_paint(float &v, float value, bool subtract) {
+  if (value < 0) {
+    if (subtract && v > 0) v = 0.0f;
+  } else {
+    v = value;
+  }
+}
+int vo_draw_regions(int nx, int ny, int nz, float *image, const float *mask, const vo_region *regions, int n,
+                    int negative_means_subtract) {
+  const bool subtract = negative_means_subtract != 0;
+  const i64 N = (i64)nx * ny * nz;
+  if (subtract && n > 0 && regions[0].value < 0) {
+    bool all_zero = true;
+    for (i64 i = 0; i < N && all_zero; i++)
+      if (!(mask && mask[i] == 0.0f) && image[i] != 0.0f) all_zero = false;
+    if (all_zero)
+      for (i64 i = 0; i < N; i++)
+        if (!(mask && mask[i] == 0.0f)) image[i] = 1.0f;
+  }
+  const int size[3] = {nx, ny, nz};
+  for (int k = 0; k < n; k++) {
+    const vo_region &r = regions[k];
+    if (r.type == 1) {
+      const float R = r.p[3];
+      const int Ri = (int)std::ceil(R - 0.5);
+      const int cx = (int)std::floor(r.p[0] + 0.5), cy = (int)std::floor(r.p[1] + 0.5), cz = (int)std::floor(r.p[2] + 0.5);
+      for (int jz = -Ri; jz <= Ri; jz++)
+        for (int jy = -Ri; jy <= Ri; jy++) {
+          const float descr = R * R - (jy * jy + jz * jz);
+          if (descr < 0.0) continue;
+          const int xr = (int)std::floor(std::sqrt(descr));
+          for (int jx = -xr; jx <= xr; jx++) {
+            const int x = cx + jx, y = cy + jy, z = cz + jz;
+            if (x < 0 || x >= nx || y < 0 || y >= ny || z < 0 || z >= nz) continue;
+            const i64 at = ((i64)z * ny + y) * nx + x;
+            if (mask && mask[at] == 0.0f) continue;
+            vo_paint(image[at], r.value, subtract);
+          }
+        }
+    } else {
+      float lo[3], hi[3];
+      for (int d = 0; d < 3; d++) {
+        lo[d] = std::max<float>((float)std::floor(r.p[2 * d] + 0.5), 0);
+        hi[d] = std::min<float>((float)std::floor(r.p[2 * d + 1] + 0.5), size[d] - 1);
+      }
+      for (int z = (int)lo[2]; z <= hi[2]; z++)
+        for (int y = (int)lo[1]; y <= hi[1]; y++)
+          for (int x = (int)lo[0]; x <= hi[0]; x++) {
+            const i64 at = ((i64)z * ny + y) * nx + x;
+            if (mask && mask[at] == 0.0f) continue;
+            vo_paint(image[at], r.value, subtract);
+          }
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Scale-space blob detection: lib/visfd/feature.hpp:56-427 (BlobDog).
 // For scale ir: LoG image into ring slot ir%3 (:170-176); for ir>=2 every voxel
 // of scale ir-1 is tested against its 80 neighbours in (x,y,z,scale): strict

@@ -19,7 +19,18 @@ void vo_tv_dense_stick(int64_t, int64_t, int64_t, const float *, const float *, 
                        float, int, float *);
 int vo_bin3d(const int64_t[3], const int64_t[3], const float *, float *, const int *);
 int vo_unbin3d(const int64_t[3], const int64_t[3], const float *, float *, const int *);
+int vo_draw_regions(int, int, int, float *, const float *, const visfd_region *, int, int);
 }
+
+// the shape of visfd::SimpleRegion<float> (lib/visfd/draw.hpp:41-87), as the caller would hand it over
+struct Region {
+  struct Rect { float xmin, xmax, ymin, ymax, zmin, zmax; };
+  struct Sphere { float x0, y0, z0, r; };
+  enum RegionType { RECT, SPHERE };
+  RegionType type = RECT;
+  union { Rect rect; Sphere sphere; } data;
+  float value = 1;
+};
 
 // pointer tables over a flat buffer; `gap` > 0 makes rows non-contiguous
 template <typename T>
@@ -204,6 +215,37 @@ int main() {
       threw = true;
     }
     check(threw, "BinArray3D throws for an offset outside [0, bin size)");
+  }
+  // DrawRegions (draw.hpp:90-237): a box, a subtracted sphere and a small bright sphere, with and
+  // without a mask, contiguous and gapped tables
+  for (int gap = 0; gap <= 3; gap += 3) {
+    const int size[3] = {31, 22, 17};
+    std::vector<Region> regions(3);
+    regions[0].type = Region::RECT;
+    regions[0].data.rect = {2.0f, 25.4f, 1.0f, 19.0f, 0.0f, 30.0f};
+    regions[0].value = 1.0f;
+    regions[1].type = Region::SPHERE;
+    regions[1].data.sphere = {14.0f, 10.0f, 8.0f, 6.5f};
+    regions[1].value = -1.0f;
+    regions[2].type = Region::SPHERE;
+    regions[2].data.sphere = {15.2f, 10.7f, 8.4f, 2.6f};
+    regions[2].value = 3.0f;
+    std::vector<visfd_region> flat(3);
+    flat[0] = {VISFD_REGION_RECT, {2.0f, 25.4f, 1.0f, 19.0f, 0.0f, 30.0f}, 1.0f};
+    flat[1] = {VISFD_REGION_SPHERE, {14.0f, 10.0f, 8.0f, 6.5f, 0.0f, 0.0f}, -1.0f};
+    flat[2] = {VISFD_REGION_SPHERE, {15.2f, 10.7f, 8.4f, 2.6f, 0.0f, 0.0f}, 3.0f};
+    for (int with_mask = 0; with_mask <= 1; with_mask++) {
+      Image3<float> img(31, 22, 17, gap), mask(31, 22, 17, gap);
+      for (int z = 0; z < 17; z++)
+        for (int y = 0; y < 22; y++)
+          for (int x = 0; x < 31; x++) mask.p()[z][y][x] = noise(rng) > -0.3f ? 1.0f : 0.0f;
+      std::vector<float> want = img.flat(), fmask = mask.flat();
+      visfd_cuda::DrawRegions(size, img.p(), with_mask ? mask.p() : nullptr, regions, true);
+      vo_draw_regions(31, 22, 17, want.data(), with_mask ? fmask.data() : nullptr, flat.data(), 3, 1);
+      char label[128];
+      std::snprintf(label, sizeof label, "DrawRegions bit-exact (row gap %d, mask %d)", gap, with_mask);
+      check(img.flat() == want, label);
+    }
   }
   std::printf("%s (%d failure%s)\n", failures ? "FAILED" : "OK", failures, failures == 1 ? "" : "s");
   return failures ? 1 : 0;

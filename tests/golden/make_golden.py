@@ -22,6 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from oracle.pyoracle import Oracle, have  # noqa: E402
 from visfd_b200 import synth  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from util import draw_cases  # noqa: E402
 
 REFERENCE = os.environ.get("VISFD_REFERENCE", "/root/reference")
 
@@ -54,6 +56,7 @@ def mrc_file_bytes(mode, nvox, data, mapcrs=(1, 2, 3), imod=None, nsymbt=0):
         hdr[38], hdr[39] = 1146047817, imod
     hdr[49:52] = np.array([1.5, -2.5, 3.5], np.float32).view(np.int32)
     return hdr.tobytes() + data.tobytes()
+
 
 
 def main():
@@ -164,6 +167,10 @@ def main():
     out["bin_aniso_off"] = ref.bin3d(bsrc, dst_shape=(4, 5, 7), offset=(1, 2, 0))
     out["unbin_2"] = ref.unbin3d(out["bin_2"], (13, 17, 22))
     out["unbin_2_off"] = ref.unbin3d(out["bin_2"], (13, 17, 22), offset=(1, 0, 1))
+
+    # ---- mask rasterisation (lib/visfd/draw.hpp:90-237) ----------------------------------------------
+    for name, (img, mask, regions, subtract) in draw_cases().items():
+        out["draw_" + name] = ref.draw_regions(img, regions, mask=mask, negative_means_subtract=subtract)
 
     # ---- MRC files (lib/mrc_simple): small files in every mode the reference reads, what its
     # MrcSimple::Read makes of them and the bytes its MrcSimple::Write produces ----------------------

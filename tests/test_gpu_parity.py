@@ -505,6 +505,62 @@ def test_c1_from_the_raw_fixture(ctx, golden):
     assert rel_err(c1["out"], golden["c1_out"]) <= TOL_SALIENCY
 
 
+def test_draw_regions_bit_exact(ctx, oracle, golden):
+    """DrawRegions (lib/visfd/draw.hpp:90-237) against the reference's own outputs, then random region
+    lists against the oracle, host and device images alike."""
+    import torch
+    from util import draw_cases
+    for name, (img, mask, regions, subtract) in draw_cases().items():
+        got = ctx.draw_regions(img, regions, mask=mask, negative_means_subtract=subtract)
+        assert np.array_equal(got, golden["draw_" + name]), name
+    rng = np.random.default_rng(6)
+    shape = (33, 70, 131)
+    for trial in range(12):
+        regions = []
+        for _ in range(int(rng.integers(1, 9))):
+            v = float(rng.choice([-1.0, 1.0, 2.5, 0.0]))
+            if rng.random() < 0.5:
+                regions.append(("sphere", float(rng.uniform(-5, 140)), float(rng.uniform(-5, 75)),
+                                float(rng.uniform(-5, 38)), float(rng.uniform(0, 30)), v))
+            else:
+                lo = rng.uniform(-6, 100, 3)
+                hi = lo + rng.uniform(-1, 60, 3)
+                regions.append(("rect", lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], v))
+        img = np.zeros(shape, np.float32) if trial % 2 else rng.standard_normal(shape).astype(np.float32)
+        mask = None if trial % 3 else (rng.random(shape) > 0.4).astype(np.float32)
+        for subtract in (False, True):
+            want = oracle.draw_regions(img, regions, mask=mask, negative_means_subtract=subtract)
+            assert np.array_equal(ctx.draw_regions(img, regions, mask=mask, negative_means_subtract=subtract), want)
+            d = torch.from_numpy(img).cuda()
+            dm = None if mask is None else torch.from_numpy(mask).cuda()
+            r = ctx.draw_regions(d, regions, mask=dm, negative_means_subtract=subtract)
+            assert r.data_ptr() == d.data_ptr() and np.array_equal(d.cpu().numpy(), want)   # in place
+    with pytest.raises(vb.VisfdCudaError):
+        ctx.draw_regions(img, [("cone", 1, 2, 3)])
+
+
+def test_draw_regions_properties_large(ctx):
+    """at a bench-like size: the voxel count of a sphere painted into zeros equals the lattice count,
+    painting is idempotent, and add-then-subtract of the same region leaves nothing"""
+    import torch
+    shape = (256, 384, 512)
+    a = torch.zeros(shape, device="cuda")
+    R = 100.3
+    ctx.draw_regions(a, [("sphere", 250.0, 190.0, 128.0, R, 1.0)])
+    ax = [np.arange(n) for n in shape]
+    jz, jy = ax[0][:, None] - 128, ax[1][None, :] - 190
+    descr = np.float32(R) * np.float32(R) - (jy * jy + jz * jz).astype(np.float32)
+    xr = np.floor(np.sqrt(np.maximum(descr, 0))).astype(np.int64)
+    count = np.where(descr >= 0, np.minimum(250 + xr, 511) - np.maximum(250 - xr, 0) + 1, 0)
+    count = np.where((np.abs(jz) <= 100) & (np.abs(jy) <= 100), count, 0).sum()
+    assert int(a.sum().item()) == int(count)
+    b = a.clone()
+    ctx.draw_regions(b, [("sphere", 250.0, 190.0, 128.0, R, 1.0)])
+    assert torch.equal(a, b)
+    ctx.draw_regions(b, [("sphere", 250.0, 190.0, 128.0, R, -1.0)], negative_means_subtract=True)
+    assert float(b.abs().max().item()) == 0.0
+
+
 def test_binning_properties_large(ctx):
     """size-independent properties at a bench-like size: a constant image stays constant, binning
     commutes with a scaling by 2, and un-binning replicates every voxel over its bin"""

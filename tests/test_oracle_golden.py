@@ -179,3 +179,36 @@ def test_reference_blob_fixture(oracle, golden):
     cli = golden["blobfix_cli"]
     for want in ((235.2, 392.0, 313.6, 177.915, -140.018), (254.8, 98.0, 274.4, 177.915, -109.148)):
         assert np.any(np.all(np.isclose(cli, want, rtol=1e-5), axis=1)), want
+
+
+def test_draw_regions(oracle, golden):
+    """DrawRegions (lib/visfd/draw.hpp:90-237): painting order, subtraction, the all-zero special case,
+    masks, fractional centres and radii, boxes clipped by the image."""
+    from util import draw_cases
+    for name, (img, mask, regions, subtract) in draw_cases().items():
+        eq(oracle.draw_regions(img, regions, mask=mask, negative_means_subtract=subtract), golden["draw_" + name])
+    # the fixture exercises what it claims to
+    g = golden["draw_add_sub"]
+    assert set(np.unique(g)) == {0.0, 0.5, 1.0, 2.0, 3.0}
+    assert golden["draw_from_ones"].min() == 0.0 and golden["draw_from_ones"][0, 23, 27] == 1.0
+    assert np.array_equal(golden["draw_empty"], draw_cases()["empty"][0])
+
+
+def test_draw_regions_vs_reference(oracle, ref_oracle):
+    rng = np.random.default_rng(5)
+    shape = (17, 19, 23)
+    for trial in range(20):
+        regions = []
+        for _ in range(int(rng.integers(1, 7))):
+            v = float(rng.choice([-1.0, 1.0, 2.5, 0.0]))
+            if rng.random() < 0.5:
+                regions.append(("sphere", *rng.uniform(-3, 25, 3).tolist(), float(rng.uniform(0, 9)), v))
+            else:
+                lo = rng.uniform(-4, 20, 3)
+                hi = lo + rng.uniform(-1, 12, 3)
+                regions.append(("rect", lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], v))
+        img = np.zeros(shape, np.float32) if trial % 2 else rng.standard_normal(shape).astype(np.float32)
+        mask = None if trial % 3 else (rng.random(shape) > 0.4).astype(np.float32)
+        for subtract in (False, True):
+            eq(oracle.draw_regions(img, regions, mask=mask, negative_means_subtract=subtract),
+               ref_oracle.draw_regions(img, regions, mask=mask, negative_means_subtract=subtract))

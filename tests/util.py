@@ -68,3 +68,26 @@ def vote_score_err(a, b, tensor_ref):
     tr = t[..., 0] + t[..., 1] + t[..., 2]
     den = np.maximum(np.maximum(np.abs(b), 0.1 * tr), 1e-3 * np.abs(b).max())
     return float((np.abs(a - b) / den).max())
+
+
+def draw_cases():
+    """name -> (image, mask, regions, negative_means_subtract); shared with the tests (imported from here)."""
+    shape = (20, 24, 28)
+    rng = np.random.default_rng(31)
+    zeros = np.zeros(shape, np.float32)
+    noisy = rng.standard_normal(shape).astype(np.float32)
+    mask = (rng.random(shape) > 0.3).astype(np.float32)
+    add_sub = [("rect", 2.0, 20.4, 3.0, 18.0, 1.0, 15.0, 1.0), ("sphere", 12.0, 10.0, 8.0, 5.0, -1.0),
+               ("sphere", 13.2, 11.7, 8.4, 2.6, 3.0), ("rect", 22.0, 40.0, -5.0, 6.49, 15.5, 30.0, 0.5),
+               ("sphere", 27.0, 23.0, 19.0, 3.5, 2.0)]
+    return {
+        "add_sub": (zeros, None, add_sub, True),
+        "from_ones": (zeros, None, [("sphere", 14.0, 12.0, 10.0, 6.3, -1.0), ("rect", 0.0, 5.0, 0.0, 5.0, 0.0, 5.0, -1.0),
+                                    ("sphere", 14.0, 12.0, 10.0, 2.0, 1.0)], True),
+        "from_ones_masked": (zeros, mask, [("rect", 3.0, 9.0, 3.0, 9.0, 3.0, 9.0, -2.0)], True),
+        "no_subtract": (noisy, None, [("sphere", 10.5, 10.5, 10.5, 4.3, -1.0), ("sphere", 5.0, 6.0, 7.0, 0.0, 9.0),
+                                      ("sphere", 20.0, 6.0, 7.0, 0.4, 8.0), ("rect", 1.5, 2.5, 0.0, 30.0, 4.0, 4.0, 7.0)], False),
+        "masked": (noisy, mask, add_sub, True),
+        "negative_first_nonzero": (noisy, None, [("sphere", 9.0, 9.0, 9.0, 5.0, -1.0)], True),
+        "empty": (noisy, None, [], True),
+    }

@@ -76,6 +76,23 @@ def _ptr(x):
     return _p(x.ctypes.data)
 
 
+REGION_DTYPE = np.dtype([("type", np.int32), ("p", np.float32, 6), ("value", np.float32)])  # struct visfd_region
+
+
+def pack_regions(regions):
+    """("rect", xmin, xmax, ymin, ymax, zmin, zmax, value) / ("sphere", x0, y0, z0, r, value) tuples ->
+    an array of `visfd_region` records (include/visfd_cuda.h; visfd::SimpleRegion<float>, draw.hpp:41-87)."""
+    rec = np.zeros(len(regions), REGION_DTYPE)
+    for i, r in enumerate(regions):
+        if r[0] == "sphere" and len(r) == 6:
+            rec[i] = (1, tuple(r[1:5]) + (0.0, 0.0), r[5])
+        elif r[0] == "rect" and len(r) == 8:
+            rec[i] = (0, tuple(r[1:7]), r[7])
+        else:
+            raise VisfdCudaError("bad region %r" % (r,))
+    return rec
+
+
 def _prep(x):
     """float32, contiguous; numpy stays numpy, torch stays torch."""
     if x is None:
@@ -412,6 +429,25 @@ class Context:
     def unbin3d(self, a, dst_shape, offset=None):
         """UnbinArray3D (lib/visfd/resample.hpp:106-166): nearest-voxel expansion to dst_shape (nz, ny, nx)."""
         return self._resample(self.lib.visfd_cuda_unbin3d, a, dst_shape, offset)
+
+    # ---- mask rasterisation ----------------------------------------------------------------------------------------
+    def draw_regions(self, image, regions, mask=None, negative_means_subtract=False):
+        """DrawRegions (lib/visfd/draw.hpp:90-237; caller bin/filter_mrc/filter_mrc.cpp:280-284).
+        regions, in painting order and in voxels: ("rect", xmin, xmax, ymin, ymax, zmin, zmax, value) or
+        ("sphere", x0, y0, z0, r, value).  A numpy image is copied and the painted copy returned; a CUDA
+        tensor is painted in place (and returned)."""
+        img = _prep(image)
+        if not _is_torch(img):
+            img = np.array(img, np.float32, order="C", copy=True)
+        mask = _prep(mask)
+        rec = pack_regions(regions)
+        self._ck(self.lib.visfd_cuda_draw_regions(self.h, *self._dims(img.shape), _ptr(img), _ptr(mask),
+                                                  rec.ctypes.data_as(C.c_void_p), _i(len(rec)),
+                                                  _i(int(negative_means_subtract))))
+        if _is_torch(image) and img.data_ptr() != image.data_ptr():
+            image.copy_(img)
+            return image
+        return img
 
     # ---- blobs -----------------------------------------------------------------------------------------------------
     def blob_dog(self, src, sigmas, delta=0.02, truncate_ratio=2.5, mask=None, minima_threshold=np.inf,

@@ -408,6 +408,19 @@ int visfd_cuda_unbin3d(visfd_ctx *ctx, const int64_t size_src[3], const int64_t 
   API_END(ctx)
 }
 
+int visfd_cuda_draw_regions(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, float *image, const float *mask,
+                            const visfd_region *regions, int n_regions, int negative_means_subtract) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz);
+  VREQUIRE(image && (regions || n_regions == 0) && n_regions >= 0, "bad argument");
+  const size_t N = (size_t)nx * ny * nz;
+  const bool host = on_host(image);
+  Staged<float> img(ctx, image, N, Dir::InOut, host), m(ctx, mask, N, Dir::In, host);
+  draw_regions_device(ctx, nx, ny, nz, img.get(), m.get(), regions, n_regions, negative_means_subtract != 0);
+  img.finish();
+  API_END(ctx)
+}
+
 int visfd_cuda_mean_stddev(visfd_ctx *ctx, int64_t n, const float *in, const float *weights, float *mean_out,
                            float *stddev_out) {
   API_BEGIN(ctx)

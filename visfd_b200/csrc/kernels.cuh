@@ -90,6 +90,11 @@ void bin3d_device(visfd_ctx *ctx, const i64 size_src[3], const i64 size_dst[3], 
 void unbin3d_device(visfd_ctx *ctx, const i64 size_src[3], const i64 size_dst[3], const float *src, float *dst,
                     const int *offset);
 
+// ---- draw.cu ----------------------------------------------------------------------
+// DrawRegions (lib/visfd/draw.hpp:90-237), in place on a device image; `regions` is a host array.
+void draw_regions_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, float *img, const float *mask,
+                         const visfd_region *regions, int n_regions, bool negative_means_subtract);
+
 // ---- blob.cu ----------------------------------------------------------------------
 struct BlobList {
   std::vector<float> crds, sigma, score;  // crds: 3 per entry (x,y,z)

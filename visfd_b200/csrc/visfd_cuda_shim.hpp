@@ -321,6 +321,32 @@ inline void UnbinArray3D(int const size_source[3], int const size_dest[3], float
   d.commit();
 }
 
+// ---- mask rasterisation (lib/visfd/draw.hpp:90-237; caller bin/filter_mrc/filter_mrc.cpp:280-284) ----
+// Region is visfd::SimpleRegion<float> (draw.hpp:41-87) or any type with the same members.
+template <typename Region>
+inline void DrawRegions(int const image_size[3], float ***aaafDest, float const *const *const *aaafMask,
+                        const std::vector<Region> &vRegions, bool negative_means_subtract = false) {
+  std::vector<visfd_region> flat(vRegions.size());
+  for (size_t i = 0; i < vRegions.size(); i++) {
+    const Region &r = vRegions[i];
+    visfd_region &f = flat[i];
+    f.value = r.value;
+    for (int k = 0; k < 6; k++) f.p[k] = 0.0f;
+    if (r.type == Region::SPHERE) {
+      f.type = VISFD_REGION_SPHERE;
+      f.p[0] = r.data.sphere.x0; f.p[1] = r.data.sphere.y0; f.p[2] = r.data.sphere.z0; f.p[3] = r.data.sphere.r;
+    } else {
+      f.type = VISFD_REGION_RECT;
+      f.p[0] = r.data.rect.xmin; f.p[1] = r.data.rect.xmax; f.p[2] = r.data.rect.ymin;
+      f.p[3] = r.data.rect.ymax; f.p[4] = r.data.rect.zmin; f.p[5] = r.data.rect.zmax;
+    }
+  }
+  Dense3<float, 1> d(image_size, aaafDest, true), m(image_size, aaafMask, false);
+  Check(visfd_cuda_draw_regions(Context(), image_size[0], image_size[1], image_size[2], d.data(), m.data(),
+                                flat.data(), (int)flat.size(), negative_means_subtract ? 1 : 0));
+  d.commit();
+}
+
 // ---- thresholds (lib/threshold/threshold.hpp; bin/filter_mrc/handlers.cpp:1037-1080) ------------
 inline void ThresholdImage(int const image_size[3], float const *const *const *aaafIn, float ***aaafOut, int kind,
                            const float t[4], float outA, float outB, float const *const *const *aaafMask = nullptr,
