@@ -340,6 +340,37 @@ def test_membrane_pipeline_vs_oracle(ctx, oracle):
     assert np.all(np.abs(want["out"][differ] - T) <= TOL_SALIENCY * T)
 
 
+def test_c4_full_size_crops_match_oracle(ctx, oracle):
+    """BASELINE config 4 at its full size (2048 x 2048 x 1024, the bench workload and seed): the oracle
+    cannot run 4.3 Gvoxel, but a crop with a margin of hw_tv + 1 + hw_gauss = 28 voxels reproduces the
+    interior exactly when it is given the full run's cut as an ABSOLUTE threshold.  Two 16^3
+    interiors: one on the membrane shell in the middle of the volume, one in the image corner (where the
+    crop's border is the image border)."""
+    import torch
+    shape = (1024, 2048, 2048)
+    sigma = float(np.float32(np.float32(5.196) / np.sqrt(3.0)))
+    tv_sigma = float(np.float32(np.float32(4.733) * np.float32(sigma)))
+    ratio = float(np.sqrt(-2.0 * np.log(0.03)))
+    vol = synth.tomogram_torch(shape, "cuda", seed=0)
+    out = torch.empty_like(vol)
+    r = ctx.membrane(vol, sigma, ratio, 1, 0.05, True, tv_sigma, 4, SQ2, out=out)
+    n = float(np.prod(shape))
+    assert abs(ctx.last_voter_count() / n - 0.05) < 1e-6
+    assert float(out.min().item()) >= 0.0 and bool(torch.isfinite(out).all().item())
+    margin, side = 28, 16
+    for corner in ((504, 1016, 1322), (0, 0, 0)):
+        lo = [max(c - margin, 0) for c in corner]
+        hi = [min(c + side + margin, s) for c, s in zip(corner, shape)]
+        crop = vol[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].contiguous().cpu().numpy()
+        want = oracle.membrane(crop, sigma, ratio, 1, r["threshold"], False, tv_sigma, 4, SQ2, want_tensor=True)
+        inner = tuple(slice(c - l, c - l + side) for c, l in zip(corner, lo))
+        got = out[corner[0]:corner[0] + side, corner[1]:corner[1] + side, corner[2]:corner[2] + side].cpu().numpy()
+        assert want["out"][inner].max() > 0
+        assert vote_score_err(got, want["out"][inner], want["tensor"][inner]) <= TOL_SALIENCY
+    del vol, out
+    torch.cuda.empty_cache()
+
+
 def test_membrane_device_path_identical(ctx):
     import torch
     vol = synth.tomogram((40, 40, 48), seed=15)
