@@ -20,6 +20,10 @@
  *    and the benchmark).  All arrays of one call must be of the same kind.
  *  - All sizes are 64-bit; the reference's `int` limits (alloc3d.hpp:33-35,
  *    multichannel_image3d.hpp:126-133) do not apply.
+ *  - DEVICE arrays: the library works on its own non-blocking stream (or the one
+ *    given to visfd_cuda_set_stream), so work the caller still has in flight on
+ *    OTHER streams that produces an input must be finished (stream or event
+ *    synchronised) before the call; outputs are complete on return.
  *  - Calls are synchronous (results are complete on return) and return 0 on
  *    success, non-zero on failure with a message in visfd_cuda_last_error().
  *    The C++ shim rethrows it as VisfdErr (lib/visfd/err_visfd.hpp:15-22).

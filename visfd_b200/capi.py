@@ -71,6 +71,11 @@ def _ptr(x):
         return None
     if _is_torch(x):
         assert x.is_cuda and x.is_contiguous() and x.dtype.is_floating_point and x.element_size() == 4
+        # The library runs on its own non-blocking stream and every entry point is synchronous
+        # (SURVEY 8b), so the only ordering the caller owes it is that whatever torch (or NCCL, through
+        # torch's stream) still has in flight for this tensor is finished before the call reads it.
+        import torch
+        torch.cuda.current_stream(x.device).synchronize()
         return _p(x.data_ptr())
     assert isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous
     return _p(x.ctypes.data)
