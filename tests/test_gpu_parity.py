@@ -452,8 +452,8 @@ def test_blob_dog_masked_vs_oracle(ctx, oracle):
 @pytest.mark.parametrize("world", [2, 3])
 def test_slab_stages_reproduce_whole_volume(ctx, world):
     """each emulated rank runs SlabMembrane's stages on its slab (own planes + raw-source
-    halo); stitched together the result equals the single-volume pipeline: the ridge
-    saliency bit for bit, the post-vote score to summation-order rounding"""
+    halo); stitched together the result equals the single-volume pipeline bit for bit: the ridge
+    saliency, the global cut and the post-vote score"""
     import torch
     from visfd_b200.slab import make_plan, distributed_cut_threshold
     shape = (60, 40, 48)
@@ -479,6 +479,10 @@ def test_slab_stages_reproduce_whole_volume(ctx, world):
         res, _ = ctx.vote_slab(sal, sm, pl.slab[0], shape[0], pl.own_local, pl.vote_local, thr, p)
         out[pl.own[0]:pl.own[1]] = res.cpu().numpy()
     assert rel_err(out, whole["out"], floor_frac=1e-2) <= 1e-5
+    # slabs and voter planes start on multiples of 8 planes (visfd_b200/slab.py, visfd_cuda_vote_slab), so
+    # every receiver meets its voters in the order of the undivided volume: identical float sums
+    assert all(pl.own[0] % 8 == 0 and pl.slab[0] % 8 == 0 for pl in plans)
+    assert np.array_equal(out, whole["out"])
 
 
 def test_vote_slab_host_delivery(ctx):

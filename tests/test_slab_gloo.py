@@ -22,8 +22,8 @@ def test_partition_and_plan():
     # C4 on 8 GPUs: gauss hw 7, tv hw 20 -> halo 28
     plans = [make_plan(1024, 8, r, 7, 20) for r in range(8)]
     assert plans[0].slab == (0, 156) and plans[0].vote == (0, 148) and plans[0].own_local == (0, 128)
-    assert plans[3].slab == (384 - 28, 512 + 28) and plans[3].vote_local == (8, 176)
-    assert plans[7].slab == (896 - 28, 1024)
+    assert plans[3].slab == (352, 512 + 28) and plans[3].vote == (364, 532) and plans[3].vote_local == (12, 180)   # 384 - 28 = 356 -> 352: brick aligned
+    assert plans[7].slab == (864, 1024)
     for r, p in enumerate(plans):
         # every send has its matching receive
         for (dst, a, b) in p.sends:

@@ -344,9 +344,15 @@ int visfd_cuda_vote_slab_host(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz
     VREQUIRE((vote_z0 >= 1 || z_offset == 0) && (vote_z1 <= nz_local - 1 || z_offset + nz_local == nz_global),
              "slab lacks the 1-plane halo around the voter planes");
     TVParams tp{p->tv_sigma, p->tv_exponent, p->tv_cutoff_ratio, 0};
-    const size_t o = plane * (size_t)vote_z0;
-    if (tv_device(ctx, nx, ny, vote_z1 - vote_z0, z_offset + vote_z0, nz_global, own_z0 - vote_z0,
-              own_z1 - vote_z0, saliency + o, threshold, nullptr, smoothed + o, p->sigma, p->eival_order,
+    // The voter list is ordered by 8^3 brick and float sums depend on the order, so the voter planes
+    // start on a GLOBAL multiple of 8 whenever the slab has the planes for it (the extra ones are out of
+    // every receiver's reach): with receiver planes that start on a multiple of 4 as well, a slab then
+    // reproduces the undivided volume bit for bit.
+    int64_t v0 = vote_z0 - (z_offset + vote_z0) % 8;
+    if (v0 < 0 || (v0 < 1 && z_offset != 0)) v0 = vote_z0;
+    const size_t o = plane * (size_t)v0;
+    if (tv_device(ctx, nx, ny, vote_z1 - v0, z_offset + v0, nz_global, own_z0 - v0,
+              own_z1 - v0, saliency + o, threshold, nullptr, smoothed + o, p->sigma, p->eival_order,
               VISFD_SCORE_PLANAR, mask ? mask + o : nullptr, mask ? mask + o : nullptr, tp, tensor, out, out_host))
       delivered = true;
   } else {

@@ -26,12 +26,16 @@ import numpy as np
 
 
 def partition(nz, world):
-    """Contiguous, near-equal plane ranges [z0, z1) per rank."""
-    base, rem = divmod(nz, world)
+    """Contiguous, near-equal plane ranges [z0, z1) per rank.  When there are at least 8 planes per rank
+    the boundaries are multiples of 8 (the last rank takes the ragged tail): the voting kernel's 4x4x4
+    receiver patches and 8^3 voter bricks then fall where they fall in the undivided volume, which makes
+    the result independent of the number of ranks bit for bit."""
+    unit = 8 if nz // 8 >= world else 1
+    base, rem = divmod(nz // unit, world)
     out, z = [], 0
     for r in range(world):
-        n = base + (1 if r < rem else 0)
-        out.append((z, z + n))
+        n = (base + (1 if r < rem else 0)) * unit
+        out.append((z, nz if r == world - 1 else z + n))
         z += n
     return out
 
@@ -42,7 +46,7 @@ class SlabPlan:
     world: int
     nz: int
     own: tuple          # global [z0, z1)
-    slab: tuple         # global [lo, hi) = own widened by halo, clipped
+    slab: tuple         # global [lo, hi) = own widened by halo, clipped, lo rounded down to a multiple of 8
     vote: tuple         # global voter range = own widened by tv_halfwidth, clipped
     halo: int
     recvs: list         # [(src_rank, global_lo, global_hi)]
@@ -62,6 +66,13 @@ def make_plan(nz, world, rank, gauss_hw, tv_hw):
     halo = (tv_hw + 1 + gauss_hw) if tv_hw > 0 else (1 + gauss_hw)
 
     def widened(r, h):
+        # The slab starts on a multiple of 8 planes: the voting stage orders its voters by 8^3 brick,
+        # and with the slab's bricks coinciding with the whole volume's every receiver meets its
+        # voters in the same order -- the multi-GPU result is then BIT-identical to the one-GPU one
+        # (float sums depend on the order), at the price of up to 7 extra halo planes.
+        return (max(0, parts[r][0] - h) // 8 * 8, min(nz, parts[r][1] + h))
+
+    def reach(r, h):
         return (max(0, parts[r][0] - h), min(nz, parts[r][1] + h))
 
     def overlap(a, b):
@@ -79,7 +90,7 @@ def make_plan(nz, world, rank, gauss_hw, tv_hw):
         o = overlap(widened(q, halo), parts[rank])
         if o:
             sends.append((q, o[0], o[1]))
-    return SlabPlan(rank, world, nz, parts[rank], slab, widened(rank, max(tv_hw, 0)), halo, recvs, sends)
+    return SlabPlan(rank, world, nz, parts[rank], slab, reach(rank, max(tv_hw, 0)), halo, recvs, sends)
 
 
 def exchange_halo(plan, own_planes, slab_buf, dist=None):
