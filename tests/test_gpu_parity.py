@@ -343,9 +343,9 @@ def test_membrane_pipeline_vs_oracle(ctx, oracle):
 def test_c4_full_size_crops_match_oracle(ctx, oracle):
     """BASELINE config 4 at its full size (2048 x 2048 x 1024, the bench workload and seed): the oracle
     cannot run 4.3 Gvoxel, but a crop with a margin of hw_tv + 1 + hw_gauss = 28 voxels reproduces the
-    interior exactly when it is given the full run's cut as an ABSOLUTE threshold.  Two 16^3
-    interiors: one on the membrane shell in the middle of the volume, one in the image corner (where the
-    crop's border is the image border)."""
+    interior exactly when it is given the full run's cut as an ABSOLUTE threshold.  Three 16^3
+    interiors: one on the membrane shell in the middle of the volume and the first and last image corners
+    (where the crop's border is the image border)."""
     import torch
     shape = (1024, 2048, 2048)
     sigma = float(np.float32(np.float32(5.196) / np.sqrt(3.0)))
@@ -358,7 +358,8 @@ def test_c4_full_size_crops_match_oracle(ctx, oracle):
     assert abs(ctx.last_voter_count() / n - 0.05) < 1e-6
     assert float(out.min().item()) >= 0.0 and bool(torch.isfinite(out).all().item())
     margin, side = 28, 16
-    for corner in ((504, 1016, 1322), (0, 0, 0)):
+    # (the first interior straddles linear voxel index 2^31, the last one ends at index 2^32 - 1)
+    for corner in ((504, 1016, 1322), (0, 0, 0), (1008, 2032, 2032)):
         lo = [max(c - margin, 0) for c in corner]
         hi = [min(c + side + margin, s) for c, s in zip(corner, shape)]
         crop = vol[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].contiguous().cpu().numpy()
@@ -367,7 +368,25 @@ def test_c4_full_size_crops_match_oracle(ctx, oracle):
         got = out[corner[0]:corner[0] + side, corner[1]:corner[1] + side, corner[2]:corner[2] + side].cpu().numpy()
         assert want["out"][inner].max() > 0
         assert vote_score_err(got, want["out"][inner], want["tensor"][inner]) <= TOL_SALIENCY
-    del vol, out
+    # the Gaussian alone at the same size (hw 7), and the 99th-percentile threshold map of the result
+    # (BASELINE config 5's last stage): bit-exact on the same three interiors
+    del out
+    smooth, _ = ctx.apply_gauss(vol, sigma, 7)
+    for corner in ((504, 1016, 1322), (0, 0, 0), (1008, 2032, 2032)):
+        lo = [max(c - 7, 0) for c in corner]
+        hi = [min(c + side + 7, s) for c, s in zip(corner, shape)]
+        crop = vol[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].contiguous().cpu().numpy()
+        want = oracle.apply_gauss(crop, sigma, 7)[0]
+        inner = tuple(slice(c - l, c - l + side) for c, l in zip(corner, lo))
+        got = smooth[corner[0]:corner[0] + side, corner[1]:corner[1] + side, corner[2]:corner[2] + side].cpu().numpy()
+        assert np.array_equal(got, want[inner])
+    m = ctx.threshold(smooth, vb.THRESH_SINGLE, [-0.01])
+    for corner in ((504, 1016, 1322), (0, 0, 0), (1008, 2032, 2032)):
+        box = tuple(slice(c, c + side) for c in corner)
+        assert np.array_equal(m[box].cpu().numpy(), oracle.threshold1(smooth[box].contiguous().cpu().numpy(), -0.01))
+    ones = int((m == 1.0).sum().item())
+    assert ones + int((m == 0.0).sum().item()) == m.numel() and 0 < ones < m.numel()
+    del vol, smooth, m
     torch.cuda.empty_cache()
 
 

@@ -786,7 +786,8 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   // finished chunk of the result can travel to the host while the next one is computed
   const i64 planes = own_z1 - own_z0;
   const bool overlap_d2h = score_host && score && planes >= 8 * BR;
-  const i64 chunk_planes = overlap_d2h ? ((planes + 7) / 8 + BR - 1) / BR * BR : planes;
+  // up to 16 chunks: only the last one's copy (1/16 of the result) is not hidden behind a kernel
+  const i64 chunk_planes = overlap_d2h ? ((planes + 15) / 16 + BR - 1) / BR * BR : planes;
   const int n_chunks = (int)((planes + chunk_planes - 1) / chunk_planes);
   VREQUIRE((i64)g.ntx * g.nty * div_up(chunk_planes, TV_TILE_Z) * 4 / TV_WARPS < 2147483647LL,
            "too many receiver tiles for one launch");
