@@ -399,16 +399,26 @@ def test_membrane_device_path_identical(ctx):
     assert ctx.last_voter_count() > 0
 
 
-def test_membrane_host_path_chunked_d2h(ctx):
+def test_membrane_host_path_chunked_d2h(ctx, monkeypatch):
     """>= 64 planes: with host arrays the voting runs in z-chunks whose results are copied back
-    behind the kernels; it must equal the single-launch device path bit for bit (70 planes:
-    a ragged last chunk)."""
+    behind the kernels; it must equal the single-launch device path bit for bit.  The library keeps
+    chunks large enough to fill the GPU for many waves, so a small test volume is only chunked when
+    VISFD_CUDA_CHUNK_WAVES lowers that bound: 70 planes -> 9 chunks of 8 planes, the last one ragged."""
     import torch
     vol = synth.tomogram((70, 24, 40), seed=16)
-    a = ctx.membrane(vol, 1.5, 2.6482, 1, 0.08, True, 4.3, 4, SQ2)
     b = ctx.membrane(torch.from_numpy(vol).cuda(), 1.5, 2.6482, 1, 0.08, True, 4.3, 4, SQ2)
-    assert np.array_equal(a["out"], b["out"].cpu().numpy())
-    assert np.count_nonzero(a["out"]) > 0
+    launches = {}
+    for waves in ("0", None):
+        if waves is None:
+            monkeypatch.delenv("VISFD_CUDA_CHUNK_WAVES", raising=False)
+        else:
+            monkeypatch.setenv("VISFD_CUDA_CHUNK_WAVES", waves)
+        before = ctx.launch_count()
+        a = ctx.membrane(vol, 1.5, 2.6482, 1, 0.08, True, 4.3, 4, SQ2)
+        launches[waves] = ctx.launch_count() - before
+        assert np.array_equal(a["out"], b["out"].cpu().numpy())
+        assert np.count_nonzero(a["out"]) > 0
+    assert launches["0"] - launches[None] == 8     # nine voting launches instead of one
 
 
 # ---- thresholds -----------------------------------------------------------------------------------------
@@ -504,7 +514,7 @@ def test_slab_stages_reproduce_whole_volume(ctx, world):
     assert np.array_equal(out, whole["out"])
 
 
-def test_vote_slab_host_delivery(ctx):
+def test_vote_slab_host_delivery(ctx, monkeypatch):
     """visfd_cuda_vote_slab_host: the host copy (chunked D2H behind the kernels when the slab owns
     >= 64 planes, one plain copy otherwise) equals the device result"""
     import torch
@@ -519,9 +529,12 @@ def test_vote_slab_host_delivery(ctx):
         sm, sal = ctx.ridge_saliency_slab(dvol[pl.slab[0]:pl.slab[1]].contiguous(), pl.slab[0], shape[0], sigma, ratio)
         thr = float(np.quantile(sal.cpu().numpy(), 0.92))
         host = np.full((pl.own[1] - pl.own[0],) + shape[1:], -1.0, np.float32)
-        res, _ = ctx.vote_slab(sal, sm, pl.slab[0], shape[0], pl.own_local, pl.vote_local, thr, p, out_host=host)
-        assert np.array_equal(host, res.cpu().numpy())
-        assert np.count_nonzero(host) > 0
+        for waves in ("0", "64"):
+            monkeypatch.setenv("VISFD_CUDA_CHUNK_WAVES", waves)
+            host[:] = -1.0
+            res, _ = ctx.vote_slab(sal, sm, pl.slab[0], shape[0], pl.own_local, pl.vote_local, thr, p, out_host=host)
+            assert np.array_equal(host, res.cpu().numpy())
+            assert np.count_nonzero(host) > 0
 
 
 # ---- binning ------------------------------------------------------------------------

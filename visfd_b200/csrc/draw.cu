@@ -107,29 +107,26 @@ void draw_regions_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, float *img, con
     }
   }
   const bool from_ones = negative_means_subtract && n_regions > 0 && regions[0].value < 0.0f;
-  int *flag = nullptr;
   const i64 n = nx * ny * nz;
+  Scratch<int> flag;
   if (from_ones) {
-    flag = static_cast<int *>(ctx->alloc(sizeof(int)));
-    VCK(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
-    any_nonzero_kernel<<<(unsigned)std::min<i64>(div_up(n, 256), 148 * 16), 256, 0, ctx->stream>>>(img, mask, n, flag);
+    flag.reset(ctx, 1);
+    VCK(cudaMemsetAsync(flag.get(), 0, sizeof(int), ctx->stream));
+    any_nonzero_kernel<<<(unsigned)std::min<i64>(div_up(n, 256), 148 * 16), 256, 0, ctx->stream>>>(img, mask, n, flag.get());
     VCK(cudaGetLastError());
+    ctx->count_launch();
   }
-  if (n_regions > 0 || from_ones) {
-    const size_t bytes = std::max<size_t>((size_t)n_regions, 1) * sizeof(PreparedRegion);
-    VREQUIRE(bytes <= 48 * 1024, "too many regions for one pass (limit 930)");
-    PreparedRegion *d_regions = static_cast<PreparedRegion *>(ctx->alloc(bytes));
-    if (n_regions > 0)
-      VCK(cudaMemcpyAsync(d_regions, prep.data(), (size_t)n_regions * sizeof(PreparedRegion), cudaMemcpyHostToDevice,
-                          ctx->stream));
-    dim3 grid(div_up(nx, 64), div_up(ny, 4), (unsigned)nz);
-    draw_regions_kernel<<<grid, 256, bytes, ctx->stream>>>(img, mask, d_regions, n_regions, (int)nx, (int)ny,
-                                                           negative_means_subtract ? 1 : 0, flag);
-    VCK(cudaGetLastError());
-    VCK(cudaStreamSynchronize(ctx->stream));  // prep[] is pageable host memory
-    ctx->release(d_regions);
-  }
-  if (flag) ctx->release(flag);
+  if (n_regions == 0) return;
+  const size_t bytes = (size_t)n_regions * sizeof(PreparedRegion);
+  VREQUIRE(bytes <= 48 * 1024, "too many regions for one pass (limit 930)");
+  Scratch<PreparedRegion> d_regions(ctx, (size_t)n_regions);
+  VCK(cudaMemcpyAsync(d_regions.get(), prep.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid(div_up(nx, 64), div_up(ny, 4), (unsigned)nz);
+  draw_regions_kernel<<<grid, 256, bytes, ctx->stream>>>(img, mask, d_regions.get(), n_regions, (int)nx, (int)ny,
+                                                         negative_means_subtract ? 1 : 0, flag.get());
+  VCK(cudaGetLastError());
+  ctx->count_launch();
+  VCK(cudaStreamSynchronize(ctx->stream));  // prep[] is pageable host memory; the scratch buffers go back to the pool
 }
 
 }  // namespace visfd_cuda

@@ -23,6 +23,8 @@
 // Epilogue (fused, accumulators still in registers): optional store of the 6-component
 // tensor (-save-progress) and DiagonalizeFlatSym3 + ScoreTensorPlanar/Linear
 // (bin/filter_mrc/handlers.cpp:1870-1892) in double.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "eigen3.cuh"
@@ -786,8 +788,14 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   // finished chunk of the result can travel to the host while the next one is computed
   const i64 planes = own_z1 - own_z0;
   const bool overlap_d2h = score_host && score && planes >= 8 * BR;
-  // up to 16 chunks: only the last one's copy (1/16 of the result) is not hidden behind a kernel
-  const i64 chunk_planes = overlap_d2h ? ((planes + 15) / 16 + BR - 1) / BR * BR : planes;
+  // up to 16 chunks: only the last one's copy (1/16 of the result) is not hidden behind a kernel;
+  // but every chunk keeps >= 64 waves of CTAs, or the tails of the launches cost more than the copy
+  // (VISFD_CUDA_CHUNK_WAVES overrides the 64, for tests that want many small chunks)
+  const char *waves_env = getenv("VISFD_CUDA_CHUNK_WAVES");
+  const i64 waves = waves_env ? std::max(0, atoi(waves_env)) : 64;
+  const i64 tiles_per_layer = (i64)div_up(nx, BR) * div_up(ny, BR);
+  const i64 min_chunk = (TV_TILE_Z * ((waves * 4 * (i64)ctx->sm_count + tiles_per_layer - 1) / tiles_per_layer) + BR - 1) / BR * BR;
+  const i64 chunk_planes = overlap_d2h ? std::max(((planes + 15) / 16 + BR - 1) / BR * BR, min_chunk) : planes;
   const int n_chunks = (int)((planes + chunk_planes - 1) / chunk_planes);
   VREQUIRE((i64)g.ntx * g.nty * div_up(chunk_planes, TV_TILE_Z) * 4 / TV_WARPS < 2147483647LL,
            "too many receiver tiles for one launch");
