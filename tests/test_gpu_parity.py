@@ -421,6 +421,32 @@ def test_membrane_host_path_chunked_d2h(ctx, monkeypatch):
     assert launches["0"] - launches[None] == 8     # nine voting launches instead of one
 
 
+def test_membrane_host_path_chunked_upload(ctx, monkeypatch):
+    """host source without a mask: upload, smoothing and ridge saliency run as a pipeline over z-chunks
+    (each a z-slab with hw+1 halo planes, uploaded behind the previous chunk's kernels).  Forced onto a
+    small volume with VISFD_CUDA_UPLOAD_CHUNK, every output must equal the single-pass device path
+    bit for bit: chunks of 8 planes (9 chunks, the last ragged), of 5 (not a multiple of anything),
+    and one larger than the halo allows to overlap (37: two chunks)."""
+    import torch
+    vol = synth.tomogram((70, 24, 40), seed=18, n_shells=2)
+    args = (1.5, 2.6482, 1, 0.08, True, 4.3, 4, SQ2)
+    want = ctx.membrane(torch.from_numpy(vol).cuda(), *args, want_saliency=True, want_direction=True, want_tensor=True)
+    for chunk in ("8", "5", "37"):
+        monkeypatch.setenv("VISFD_CUDA_UPLOAD_CHUNK", chunk)
+        before = ctx.launch_count()
+        got = ctx.membrane(vol, *args, want_saliency=True, want_direction=True, want_tensor=True)
+        n_chunks = -(-70 // int(chunk))
+        assert ctx.launch_count() - before >= 4 * n_chunks      # 3 sweeps + ridge per chunk
+        assert np.float32(got["threshold"]) == np.float32(want["threshold"])
+        for k in ("out", "hess_saliency", "direction", "tensor"):
+            assert np.array_equal(got[k], want[k].cpu().numpy()), (chunk, k)
+        # and without voting (the saliency lands in `out`)
+        a = ctx.membrane(vol, 1.5, 2.6482, 1, 0.08, True, 0.0, 4, SQ2)
+        monkeypatch.delenv("VISFD_CUDA_UPLOAD_CHUNK")
+        b = ctx.membrane(vol, 1.5, 2.6482, 1, 0.08, True, 0.0, 4, SQ2)
+        assert np.array_equal(a["out"], b["out"])
+
+
 # ---- thresholds -----------------------------------------------------------------------------------------
 def test_thresholds_bit_exact(ctx, oracle, golden):
     x = golden["thr_x"]

@@ -2,6 +2,8 @@
 // checks, host<->device staging for the drop-in (host pointer) path, error mapping.
 // All compute is in the other translation units; nothing here runs on the CPU except
 // parameter generation (taps, half-widths), which the reference also does on the host.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include <cmath>
@@ -253,6 +255,68 @@ int visfd_cuda_tv_dense_stick(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz
 }
 
 // ---- fused membrane pipeline ------------------------------------------------------------------------
+// Host-resident source, no mask: upload + smoothing + ridge saliency as a pipeline over z-chunks, so
+// that only the first chunk's upload is exposed (the chunk's planes plus hw+1 halo planes travel on the
+// copy stream into one of two staging slabs while the previous chunk is smoothed and scored) and the
+// source never has to be resident as a whole.  Every chunk is a z-slab in the sense of the header
+// (global borders only at the global ends), so smoothed/saliency/direction are bit-identical to the
+// single-pass result.  Returns false (nothing done) when the volume is too small to be worth it.
+static bool upload_smooth_ridge_chunked(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src_host,
+                                        const visfd_membrane_params *p, float *smoothed, float *saliency,
+                                        float *direction) {
+  const int h = (int)floor(p->sigma * p->truncate_ratio);
+  VREQUIRE(h >= 0, "negative Gaussian half-width");
+  const int64_t halo = h + 1;
+  const char *env = getenv("VISFD_CUDA_UPLOAD_CHUNK");       // planes per chunk (tests: small chunks)
+  int64_t cz = env ? std::max(1, atoi(env)) : std::max<int64_t>(64, ((nz + 15) / 16 + 7) / 8 * 8);
+  if (!env && (nz < 2 * cz || nx * ny < (1 << 16))) return false;
+  if (nz < 3 || cz >= nz) return false;
+  const size_t plane = (size_t)nx * (size_t)ny;
+  const int64_t slab_max = std::min<int64_t>(nz, cz + 2 * halo);
+  Scratch<float> stage0(ctx, (size_t)slab_max * plane), stage1(ctx, (size_t)slab_max * plane);
+  Scratch<float> slab_sm(ctx, (size_t)slab_max * plane);
+  float *stage[2] = {stage0.get(), stage1.get()};
+  if (!ctx->copy_stream) VCK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  const int n_chunks = (int)((nz + cz - 1) / cz);
+  std::vector<cudaEvent_t> uploaded((size_t)n_chunks), consumed((size_t)n_chunks);
+  for (int c = 0; c < n_chunks; c++) {
+    VCK(cudaEventCreateWithFlags(&uploaded[(size_t)c], cudaEventDisableTiming));
+    VCK(cudaEventCreateWithFlags(&consumed[(size_t)c], cudaEventDisableTiming));
+  }
+  const float sg[3] = {p->sigma, p->sigma, p->sigma};
+  const int hw[3] = {h, h, h};
+  // the staging slabs come from the stream-ordered pool: whatever used them last ran on ctx->stream
+  cudaEvent_t start;
+  VCK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+  VCK(cudaEventRecord(start, ctx->stream));
+  VCK(cudaStreamWaitEvent(ctx->copy_stream, start, 0));
+  for (int c = 0; c < n_chunks; c++) {
+    const int64_t c0 = (int64_t)c * cz, c1 = std::min(nz, c0 + cz);
+    const int64_t lo = std::max<int64_t>(0, c0 - halo), hi = std::min(nz, c1 + halo);
+    float *buf = stage[c & 1];
+    if (c >= 2) VCK(cudaStreamWaitEvent(ctx->copy_stream, consumed[(size_t)c - 2], 0));
+    VCK(cudaMemcpyAsync(buf, src_host + (size_t)lo * plane, (size_t)(hi - lo) * plane * sizeof(float),
+                        cudaMemcpyHostToDevice, ctx->copy_stream));
+    VCK(cudaEventRecord(uploaded[(size_t)c], ctx->copy_stream));
+    VCK(cudaStreamWaitEvent(ctx->stream, uploaded[(size_t)c], 0));
+    gauss_device(ctx, nx, ny, hi - lo, lo, nz, buf, slab_sm.get(), nullptr, sg, hw, true, nullptr, 1.0f);
+    VCK(cudaEventRecord(consumed[(size_t)c], ctx->stream));
+    VCK(cudaMemcpyAsync(smoothed + (size_t)c0 * plane, slab_sm.get() + (size_t)(c0 - lo) * plane,
+                        (size_t)(c1 - c0) * plane * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    // slab-local planes [c0-lo, c1-lo) of a saliency / direction array whose plane 0 is global plane lo
+    ridge_device(ctx, nx, ny, hi - lo, lo, nz, c0 - lo, c1 - lo, slab_sm.get(), nullptr, p->sigma, p->eival_order,
+                 VISFD_SCORE_PLANAR, saliency + (size_t)lo * plane, direction ? direction + 3 * (size_t)lo * plane : nullptr);
+  }
+  VCK(cudaStreamSynchronize(ctx->copy_stream));
+  VCK(cudaStreamSynchronize(ctx->stream));   // before the staging slabs go back to the pool
+  for (int c = 0; c < n_chunks; c++) {
+    cudaEventDestroy(uploaded[(size_t)c]);
+    cudaEventDestroy(consumed[(size_t)c]);
+  }
+  cudaEventDestroy(start);
+  return true;
+}
+
 int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src,
                         const float *mask, const visfd_membrane_params *p, float *out,
                         float *hess_saliency, float *direction, float *tensor, float *threshold_out) {
@@ -261,7 +325,7 @@ int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, cons
   VREQUIRE(src && p && out, "NULL argument");
   const size_t N = (size_t)nx * ny * nz;
   const bool host = on_host(src);
-  Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host);
+  Staged<float> m(ctx, mask, N, Dir::In, host);
   Staged<float> o(ctx, out, N, Dir::Out, host);
   Staged<float> hs(ctx, hess_saliency, N, Dir::Out, host);
   Staged<float> dir(ctx, direction, 3 * N, mask ? Dir::InOut : Dir::Out, host);
@@ -269,15 +333,19 @@ int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, cons
   const bool vote = p->tv_sigma > 0.0f;
 
   Scratch<float> sm(ctx, N);
-  smooth_for_hessian(ctx, nx, ny, nz, 0, nz, s.get(), m.get(), p->sigma, p->truncate_ratio, sm.get());
   // saliency lives in `out` when there is no voting, else in hess_saliency's buffer or scratch
   Scratch<float> sal_scratch;
   float *sal = nullptr;
   if (!vote) sal = o.get();
   else if (hs.get()) sal = hs.get();
   else { sal_scratch.reset(ctx, N); sal = sal_scratch.get(); }
-  ridge_device(ctx, nx, ny, nz, 0, nz, 0, nz, sm.get(), m.get(), p->sigma, p->eival_order,
-               VISFD_SCORE_PLANAR, sal, dir.get());
+  if (!(host && !mask && upload_smooth_ridge_chunked(ctx, nx, ny, nz, src, p, sm.get(), sal, dir.get()))) {
+    Staged<float> s(ctx, src, N, Dir::In, host);
+    smooth_for_hessian(ctx, nx, ny, nz, 0, nz, s.get(), m.get(), p->sigma, p->truncate_ratio, sm.get());
+    ridge_device(ctx, nx, ny, nz, 0, nz, 0, nz, sm.get(), m.get(), p->sigma, p->eival_order,
+                 VISFD_SCORE_PLANAR, sal, dir.get());
+    // (the pool is stream-ordered: the staged source may be recycled once the work above is queued)
+  }
   float thr = p->cut;
   if (p->cut_is_fraction) thr = select_threshold_device(ctx, N, sal, m.get(), p->cut);
   if (threshold_out) *threshold_out = thr;
