@@ -361,10 +361,10 @@ __device__ __forceinline__ int axis_gap(int lo_a, int hi_a, int lo_b, int hi_b) 
 }
 
 constexpr int TV_DRAIN = 32;             // voters evaluated per drain
-constexpr int TV_NC = 2;                 // candidates tested per lane and streaming iteration (3: no faster)
-// ring capacity: at most TV_DRAIN - 1 + 32 * TV_NC voters are queued when an iteration starts, and it adds
-// up to 32 * TV_NC more before the whole batches among the former are drained
-constexpr int TV_QCAP = (2 * TV_NC + 1) * TV_DRAIN;
+// ring capacity: at most TV_DRAIN - 1 + 64 voters are queued when a streaming iteration (64 candidates,
+// two per lane; three per lane measured no faster) starts, and it adds up to 64 more before the whole
+// batches among the former are drained
+constexpr int TV_QCAP = 5 * TV_DRAIN;
 constexpr float TV_R2_EPS = 1e-30f;      // keeps 1/r^2 finite for the self vote (r = 0, d.n = 0)
 
 __device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }  // FFMA2 takes scalar (.F32) operands
@@ -598,36 +598,26 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
     gi = locate(min(e, total - 1));
     a = __ldg(&g.rec[gi].a);
   };
-  uint32_t ng[TV_NC];
-  float4 na[TV_NC];
-#pragma unroll
-  for (int c = 0; c < TV_NC; c++) {
-    ng[c] = 0;
-    na[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (total > 0) fetch(32 * c + lane, ng[c], na[c]);
+  uint32_t ng0 = 0, ng1 = 0;
+  float4 na0 = make_float4(0.f, 0.f, 0.f, 0.f), na1 = na0;
+  if (total > 0) {
+    fetch(lane, ng0, na0);
+    fetch(32 + lane, ng1, na1);
   }
-  for (uint32_t base = 0; base < total; base += 32 * TV_NC) {
-    float4 a[TV_NC];
-    uint32_t gi[TV_NC];
-#pragma unroll
-    for (int c = 0; c < TV_NC; c++) {
-      a[c] = na[c];
-      gi[c] = ng[c];
-    }
-#pragma unroll
-    for (int c = 0; c < TV_NC; c++) fetch(base + 32 * (TV_NC + c) + lane, ng[c], na[c]);
+  for (uint32_t base = 0; base < total; base += 64) {
+    const float4 a0 = na0, a1 = na1;
+    const uint32_t g0 = ng0, g1 = ng1;
+    fetch(base + 64 + lane, ng0, na0);
+    fetch(base + 96 + lane, ng1, na1);
+    const bool p0 = base + lane < total && reach(a0), p1 = base + 32 + lane < total && reach(a1);
+    const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
     const unsigned below = (1u << lane) - 1u;
-    int added = 0;
-#pragma unroll
-    for (int c = 0; c < TV_NC; c++) {
-      const bool p = base + 32 * c + lane < total && reach(a[c]);
-      const unsigned m = __ballot_sync(0xffffffffu, p);
-      if (p) enqueue(head + cnt + added + __popc(m & below), gi[c]);
-      added += __popc(m);
-    }
+    const int n0 = __popc(m0);
+    if (p0) enqueue(head + cnt + __popc(m0 & below), g0);
+    if (p1) enqueue(head + cnt + n0 + __popc(m1 & below), g1);
     cp_async_commit();
     const int ndrain = cnt & ~(TV_DRAIN - 1);   // whole drains among the voters queued BEFORE this iteration
-    cnt += added;
+    cnt += n0 + __popc(m1);
     if (ndrain) {
       cp_async_wait<1>();
       __syncwarp();
