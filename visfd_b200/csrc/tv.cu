@@ -35,9 +35,9 @@ namespace visfd_cuda {
 
 constexpr int BR = 8;            // brick edge
 constexpr int BR3 = BR * BR * BR;
-// Warps never synchronise with each other; four per CTA cover one 8x8x4 receiver tile.  (One-warp CTAs
-// would release registers and shared memory warp by warp instead of when the slowest of four is done
-// -- 14 of 16 warp slots are occupied on average -- but measured 3 % slower: 32.0 against 31.0 ms.)
+// Warps never synchronise with each other; four per CTA cover one 8x8x4 receiver tile and share its
+// candidates in L1.  Measured on the 256^3 run: 1 warp per CTA 32.0 ms, 2: 29.6, 4: 29.5, 8: 30.6
+// (fewer: less sharing; more: registers and shared memory wait for the slowest of eight patches).
 constexpr int TV_WARPS = 4;
 constexpr int TV_THREADS = 32 * TV_WARPS;
 constexpr int TV_MIN_CTAS = 16 / TV_WARPS;
