@@ -336,6 +336,28 @@ int visfd_cuda_blob_dog(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
                         float *min_sigma, float *min_score, int64_t *n_minima,
                         float *max_crds, float *max_sigma, float *max_score,
                         int64_t *n_maxima);
+/* Z-slab form for the multi-GPU driver.  The slab holds image planes
+ * [z_offset, z_offset + nz_local) and must carry, around the receiver planes [own_z0, own_z1)
+ * (slab-local), a halo of (largest LoG half-width + 1) planes wherever the slab does not end at the
+ * image border.  Candidates are reported for the receiver planes only, z as the IMAGE plane index,
+ * ordered by (scale, z, y, x), after the absolute thresholds but BEFORE the ratio thresholds, which
+ * need the best scores of the whole image (feature.hpp:341-344, :369-372): best_scores[0] /
+ * best_scores[1] receive this slab's best minimum / maximum score (1 / -1 if none).  The caller
+ * all-reduces them (min / max), concatenates the ranks' lists per scale in rank order and finishes
+ * with visfd_cuda_blob_finalize.  src / mask: DEVICE pointers; lists: HOST buffers. */
+int visfd_cuda_blob_dog_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
+                             int64_t nz_global, int64_t own_z0, int64_t own_z1, const float *src,
+                             const float *mask, const float *sigmas, int n_sigmas, float delta,
+                             float truncate_ratio, float minima_threshold, float maxima_threshold,
+                             int use_threshold_ratios, int64_t capacity, float *min_crds,
+                             float *min_sigma, float *min_score, int64_t *n_minima, float *max_crds,
+                             float *max_sigma, float *max_score, int64_t *n_maxima, float *best_scores);
+/* The final score filter of BlobDog (feature.hpp:362-417) on gathered HOST lists, in place;
+ * *n_minima / *n_maxima: lengths in, lengths out. */
+int visfd_cuda_blob_finalize(float minima_threshold, float maxima_threshold, int use_threshold_ratios,
+                             float best_min_score, float best_max_score, float *min_crds,
+                             float *min_sigma, float *min_score, int64_t *n_minima, float *max_crds,
+                             float *max_sigma, float *max_score, int64_t *n_maxima);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,23 @@ def main():
                 bad = np.argwhere(got != want)
                 print("  first differing voxels (z,y,x):", bad[:5].tolist(), "count", len(bad), flush=True)
             ok = ok and same
+    # ---- scale-space blob detection over the same ranks (all-gathered lists, all-reduced best scores) ----
+    from visfd_b200.slab import SlabBlobs
+    bshape = (max(192, 48 * world), 80, 96)
+    sigmas = (1.5 * 1.25 ** np.arange(6)).astype(np.float32)
+    bvol = synth.tomogram(bshape, seed=50, n_shells=0, blobs=60, blob_sigma=(1.5, 4.0))
+    o0, o1 = partition(bshape[0], world)[rank]
+    for kw in (dict(minima_threshold=0.3, maxima_threshold=0.3, use_threshold_ratios=True),
+               dict(minima_threshold=0.0, maxima_threshold=-np.inf, use_threshold_ratios=False)):
+        blobs = SlabBlobs(ctx, bshape, sigmas, 0.02, ratio, rank=rank, world=world, dist=dist, device=dev)
+        own = torch.from_numpy(bvol[o0:o1]).to(dev, non_blocking=True)
+        got = blobs.run(own, **kw)
+        if rank == 0:
+            want = ctx.blob_dog(torch.from_numpy(bvol).to(dev), sigmas, 0.02, ratio, **kw)
+            same = np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+            print(f"blobs ({'ratio' if kw['use_threshold_ratios'] else 'absolute'} thresholds): world {world}, shape {bshape}, "
+                  f"{len(want[0])} minima, {len(want[1])} maxima: {'identical' if same else 'DIFFERENT'}", flush=True)
+            ok = ok and same and len(want[0]) > 0
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()

@@ -540,6 +540,38 @@ def test_slab_stages_reproduce_whole_volume(ctx, world):
     assert np.array_equal(out, whole["out"])
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_blob_slabs_reproduce_whole_volume(ctx, oracle, world):
+    """visfd_cuda_blob_dog_slab on each emulated rank's slab (own planes + LoG halo), lists concatenated per
+    scale in rank order, best scores reduced, visfd_cuda_blob_finalize == BlobDog on the whole volume (and the
+    oracle), rows and order, for ratio and absolute thresholds"""
+    import torch
+    from visfd_b200.slab import make_plan, log_halfwidth, _concat_by_scale
+    shape = (61, 40, 52)
+    vol = synth.tomogram(shape, seed=19, n_shells=0, blobs=30, blob_sigma=(1.0, 3.0))
+    dvol = torch.from_numpy(vol).cuda()
+    sigmas = (1.0 * 1.25 ** np.arange(6)).astype(np.float32)
+    hw = max(log_halfwidth(s, 0.02, 2.6482) for s in sigmas)
+    plans = [make_plan(shape[0], world, r, hw, 0) for r in range(world)]
+    for kw in (dict(minima_threshold=0.3, maxima_threshold=0.3, use_threshold_ratios=True),
+               dict(minima_threshold=0.0, maxima_threshold=-np.inf, use_threshold_ratios=False)):
+        whole = ctx.blob_dog(dvol, sigmas, 0.02, 2.6482, **kw)
+        want = oracle.blob_dog(vol, sigmas, 0.02, 2.6482, **kw)
+        parts = [ctx.blob_dog_slab(dvol[pl.slab[0]:pl.slab[1]].contiguous(), pl.slab[0], shape[0], pl.own_local, sigmas,
+                                   0.02, 2.6482, **kw) for pl in plans]
+        best = (min(p[2][0] for p in parts), max(p[2][1] for p in parts))
+        got = ctx.blob_finalize(_concat_by_scale([p[0] for p in parts], sigmas),
+                                _concat_by_scale([p[1] for p in parts], sigmas), best, **kw)
+        for k in (0, 1):
+            assert np.array_equal(got[k], whole[k]) and np.array_equal(got[k], want[k])
+        assert len(got[0]) > 0
+    # a slab without the halo is refused, not silently wrong
+    pl = plans[1]
+    with pytest.raises(vb.VisfdCudaError):
+        ctx.blob_dog_slab(dvol[pl.own[0]:pl.own[1]].contiguous(), pl.own[0], shape[0], (0, pl.own[1] - pl.own[0]), sigmas,
+                          0.02, 2.6482)
+
+
 def test_vote_slab_host_delivery(ctx, monkeypatch):
     """visfd_cuda_vote_slab_host: the host copy (chunked D2H behind the kernels when the slab owns
     >= 64 planes, one plain copy otherwise) equals the device result"""

@@ -98,6 +98,66 @@ class OracleBackend:
         return torch.from_numpy(sc[a:b].copy()), torch.from_numpy(t[a:b].copy())
 
 
+    def blob_dog_slab(self, src, z_offset, nz_global, own, sigmas, delta, truncate_ratio, mask=None, capacity=0,
+                      minima_threshold=np.inf, maxima_threshold=-np.inf, use_threshold_ratios=True):
+        """the oracle on the slab, unfiltered; candidates of the own planes only, z as image plane.  A slab
+        end inside the image is `image border` to the oracle, which only discards candidates on the slab's
+        first / last plane -- never own planes, thanks to the halo."""
+        a = src.numpy()
+        kw = dict(minima_threshold=minima_threshold, maxima_threshold=maxima_threshold, use_threshold_ratios=False)
+        if use_threshold_ratios:   # ratio thresholds are applied by blob_finalize
+            kw = dict(minima_threshold=0.0, maxima_threshold=0.0, use_threshold_ratios=False)
+        mn, mx = self.o.blob_dog(a, sigmas, delta, truncate_ratio, **kw)
+        out = []
+        for rows in (mn, mx):
+            rows = rows[(rows[:, 2] >= own[0]) & (rows[:, 2] < own[1])].copy()
+            rows[:, 2] += z_offset
+            out.append(rows)
+        best = (min([1.0] + out[0][:, 4].tolist()), max([-1.0] + out[1][:, 4].tolist()))
+        return out[0], out[1], best
+
+    def blob_finalize(self, mins, maxs, best, **kw):
+        return self.vb.capi.blob_finalize(mins, maxs, best, lib=self.lib, **kw)
+
+
+def _blob_worker(rank, world, port, shape, seed, sigmas, kw, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from visfd_b200 import synth
+        from visfd_b200.slab import SlabBlobs
+        pipe = SlabBlobs(OracleBackend(), shape, sigmas, 0.02, 2.6482, rank=rank, world=world, dist=dist, device="cpu")
+        z0, z1 = pipe.plan.own
+        own = torch.from_numpy(synth.tomogram(shape, seed=seed, z0=z0, z1=z1, n_shells=0, blobs=12, blob_sigma=(1.0, 2.5)))
+        ret[rank] = pipe.run(own, **kw)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_blobs_match_single_process(world):
+    """SlabBlobs over gloo: halo exchange, per-slab scan, all-gather of the lists, all-reduce of the best
+    scores, final ratio filter == BlobDog on the whole volume, rows and order included."""
+    import torch.multiprocessing as mp
+    from oracle.pyoracle import Oracle
+    from visfd_b200 import synth
+    shape, seed = (30, 18, 20), 9
+    sigmas = 1.0 * 1.3 ** np.arange(5)
+    vol = synth.tomogram(shape, seed=seed, n_shells=0, blobs=12, blob_sigma=(1.0, 2.5))
+    for kw in (dict(minima_threshold=0.4, maxima_threshold=0.4, use_threshold_ratios=True),
+               dict(minima_threshold=0.0, maxima_threshold=-np.inf, use_threshold_ratios=False)):
+        port = 29700 + world + os.getpid() % 200
+        ret = mp.Manager().dict()
+        mp.spawn(_blob_worker, args=(world, port, shape, seed, sigmas, kw, ret), nprocs=world, join=True)
+        want = Oracle("port").blob_dog(vol, sigmas, 0.02, 2.6482, **kw)
+        assert len(want[0]) > 0
+        for r in range(world):                      # every rank ends up with the whole list
+            assert np.array_equal(ret[r][0], want[0]) and np.array_equal(ret[r][1], want[1])
+
+
 def _worker(rank, world, port, shape, seed, ret):
     import torch
     import torch.distributed as dist

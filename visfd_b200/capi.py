@@ -98,6 +98,33 @@ def pack_regions(regions):
     return rec
 
 
+def _pack_blobs(c, s, sc, n):
+    return np.concatenate([c[:n], s[:n, None], sc[:n, None]], axis=1)
+
+
+def blob_finalize(minima, maxima, best, minima_threshold=np.inf, maxima_threshold=-np.inf,
+                  use_threshold_ratios=True, lib=None):
+    """The final score filter of BlobDog on (n, 5) candidate rows x,y,z,sigma,score (host only, no GPU)."""
+    lib = lib or load_library()
+    out, cols, counts = [], [], []
+    for rows in (minima, maxima):
+        rows = np.ascontiguousarray(rows, np.float32).reshape(-1, 5)
+        c = np.ascontiguousarray(rows[:, :3])
+        sg = np.ascontiguousarray(rows[:, 3])
+        sc = np.ascontiguousarray(rows[:, 4])
+        cols.append((c, sg, sc))
+        counts.append(_i64(len(rows)))
+    rc = lib.visfd_cuda_blob_finalize(_f(minima_threshold), _f(maxima_threshold), _i(int(use_threshold_ratios)),
+                                      _f(best[0]), _f(best[1]), _ptr(cols[0][0]), _ptr(cols[0][1]), _ptr(cols[0][2]),
+                                      C.byref(counts[0]), _ptr(cols[1][0]), _ptr(cols[1][1]), _ptr(cols[1][2]),
+                                      C.byref(counts[1]))
+    if rc != 0:
+        raise VisfdCudaError(lib.visfd_cuda_last_error().decode())
+    for (c, sg, sc), n in zip(cols, counts):
+        out.append(_pack_blobs(c, sg, sc, n.value))
+    return out[0], out[1]
+
+
 def _prep(x):
     """float32, contiguous; numpy stays numpy, torch stays torch."""
     if x is None:
@@ -469,7 +496,34 @@ class Context:
                                               _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]), C.byref(nmin),
                                               _ptr(bufs[3]), _ptr(bufs[4]), _ptr(bufs[5]), C.byref(nmax)))
         a, b = min(nmin.value, capacity), min(nmax.value, capacity)
+        return _pack_blobs(bufs[0], bufs[1], bufs[2], a), _pack_blobs(bufs[3], bufs[4], bufs[5], b)
 
-        def pack(c, s, sc, n):
-            return np.concatenate([c[:n], s[:n, None], sc[:n, None]], axis=1)
-        return pack(bufs[0], bufs[1], bufs[2], a), pack(bufs[3], bufs[4], bufs[5], b)
+    def blob_dog_slab(self, src, z_offset, nz_global, own, sigmas, delta=0.02, truncate_ratio=2.5, mask=None,
+                      minima_threshold=np.inf, maxima_threshold=-np.inf, use_threshold_ratios=True,
+                      capacity=1 << 20):
+        """visfd_cuda_blob_dog_slab: BlobDog on a z-slab (device tensor; own = slab-local receiver planes).
+        -> (minima, maxima, (best_min, best_max)): candidate rows x,y,z(image),sigma,score BEFORE the final
+        filter, and this slab's best scores (see blob_finalize)."""
+        src, mask = _prep(src), _prep(mask)
+        sg = np.ascontiguousarray(np.asarray(sigmas), np.float32)
+        bufs = [np.zeros((capacity, 3), np.float32), np.zeros(capacity, np.float32), np.zeros(capacity, np.float32),
+                np.zeros((capacity, 3), np.float32), np.zeros(capacity, np.float32), np.zeros(capacity, np.float32)]
+        nmin, nmax = _i64(), _i64()
+        best = (_f * 2)()
+        self._ck(self.lib.visfd_cuda_blob_dog_slab(self.h, *self._dims(src.shape), _i64(z_offset), _i64(nz_global),
+                                                   _i64(own[0]), _i64(own[1]), _ptr(src), _ptr(mask), _ptr(sg),
+                                                   _i(len(sg)), _f(delta), _f(truncate_ratio), _f(minima_threshold),
+                                                   _f(maxima_threshold), _i(int(use_threshold_ratios)),
+                                                   _i64(capacity), _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]),
+                                                   C.byref(nmin), _ptr(bufs[3]), _ptr(bufs[4]), _ptr(bufs[5]),
+                                                   C.byref(nmax), best))
+        if nmin.value > capacity or nmax.value > capacity:
+            raise VisfdCudaError("blob candidate lists exceed the capacity given")
+        return (_pack_blobs(bufs[0], bufs[1], bufs[2], nmin.value), _pack_blobs(bufs[3], bufs[4], bufs[5], nmax.value),
+                (best[0], best[1]))
+
+    def blob_finalize(self, minima, maxima, best, minima_threshold=np.inf, maxima_threshold=-np.inf,
+                      use_threshold_ratios=True):
+        """visfd_cuda_blob_finalize: the final score filter (feature.hpp:362-417) on gathered candidate rows,
+        given the best scores of the whole image."""
+        return blob_finalize(minima, maxima, best, minima_threshold, maxima_threshold, use_threshold_ratios, self.lib)

@@ -34,6 +34,15 @@ static void check_dims(int64_t nx, int64_t ny, int64_t nz) {
 
 static bool on_host(const void *p) { return p != nullptr && !is_device_pointer(p); }
 
+static void emit_blob_list(const BlobList &l, int64_t capacity, float *crds, float *sg, float *sc, int64_t *cnt) {
+  int64_t n = (int64_t)l.score.size();
+  if (cnt) *cnt = n;
+  int64_t k = std::min(n, capacity);
+  if (crds && k) memcpy(crds, l.crds.data(), 3 * k * sizeof(float));
+  if (sg && k) memcpy(sg, l.sigma.data(), k * sizeof(float));
+  if (sc && k) memcpy(sc, l.score.data(), k * sizeof(float));
+}
+
 extern "C" {
 
 // ---- host-side parameter helpers ---------------------------------------------------------
@@ -519,19 +528,57 @@ int visfd_cuda_blob_dog(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, cons
   const bool host = on_host(src);
   Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host);
   BlobList mins, maxs;
-  blob_dog_device(ctx, nx, ny, nz, s.get(), m.get(), sigmas, n_sigmas, delta, truncate_ratio, minima_threshold,
-                  maxima_threshold, use_threshold_ratios, mins, maxs);
-  auto emit = [&](const BlobList &l, float *crds, float *sg, float *sc, int64_t *cnt) {
-    int64_t n = (int64_t)l.score.size();
-    if (cnt) *cnt = n;
-    int64_t k = std::min(n, capacity);
-    if (crds && k) memcpy(crds, l.crds.data(), 3 * k * sizeof(float));
-    if (sg && k) memcpy(sg, l.sigma.data(), k * sizeof(float));
-    if (sc && k) memcpy(sc, l.score.data(), k * sizeof(float));
-  };
-  emit(mins, min_crds, min_sigma, min_score, n_minima);
-  emit(maxs, max_crds, max_sigma, max_score, n_maxima);
+  blob_dog_device(ctx, nx, ny, nz, 0, nz, 0, nz, s.get(), m.get(), sigmas, n_sigmas, delta, truncate_ratio,
+                  minima_threshold, maxima_threshold, use_threshold_ratios, mins, maxs, true, nullptr);
+  emit_blob_list(mins, capacity, min_crds, min_sigma, min_score, n_minima);
+  emit_blob_list(maxs, capacity, max_crds, max_sigma, max_score, n_maxima);
   API_END(ctx)
+}
+
+int visfd_cuda_blob_dog_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
+                             int64_t nz_global, int64_t own_z0, int64_t own_z1, const float *src, const float *mask,
+                             const float *sigmas, int n_sigmas, float delta, float truncate_ratio,
+                             float minima_threshold, float maxima_threshold, int use_threshold_ratios,
+                             int64_t capacity, float *min_crds, float *min_sigma, float *min_score,
+                             int64_t *n_minima, float *max_crds, float *max_sigma, float *max_score,
+                             int64_t *n_maxima, float *best_scores) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz_local);
+  VREQUIRE(src && sigmas && n_sigmas >= 0 && capacity >= 0 && best_scores, "bad arguments");
+  VREQUIRE(is_device_pointer(src) && (!mask || is_device_pointer(mask)), "slab entry points take device pointers only");
+  BlobList mins, maxs;
+  blob_dog_device(ctx, nx, ny, nz_local, z_offset, nz_global, own_z0, own_z1, src, mask, sigmas, n_sigmas, delta,
+                  truncate_ratio, minima_threshold, maxima_threshold, use_threshold_ratios, mins, maxs, false,
+                  best_scores);
+  emit_blob_list(mins, capacity, min_crds, min_sigma, min_score, n_minima);
+  emit_blob_list(maxs, capacity, max_crds, max_sigma, max_score, n_maxima);
+  API_END(ctx)
+}
+
+int visfd_cuda_blob_finalize(float minima_threshold, float maxima_threshold, int use_threshold_ratios,
+                             float best_min_score, float best_max_score, float *min_crds, float *min_sigma,
+                             float *min_score, int64_t *n_minima, float *max_crds, float *max_sigma,
+                             float *max_score, int64_t *n_maxima) {
+  try {
+    VREQUIRE(n_minima && n_maxima && *n_minima >= 0 && *n_maxima >= 0, "bad arguments");
+    auto load = [](const float *crds, const float *sg, const float *sc, int64_t n) {
+      BlobList l;
+      VREQUIRE(n == 0 || (crds && sg && sc), "NULL list");
+      l.crds.assign(crds, crds + 3 * n);
+      l.sigma.assign(sg, sg + n);
+      l.score.assign(sc, sc + n);
+      return l;
+    };
+    BlobList mins = load(min_crds, min_sigma, min_score, *n_minima), maxs = load(max_crds, max_sigma, max_score, *n_maxima);
+    blob_final_filter(mins, maxs, minima_threshold, maxima_threshold, use_threshold_ratios, best_min_score,
+                      best_max_score);
+    emit_blob_list(mins, *n_minima, min_crds, min_sigma, min_score, n_minima);
+    emit_blob_list(maxs, *n_maxima, max_crds, max_sigma, max_score, n_maxima);
+    return 0;
+  } catch (const std::exception &ex) {
+    set_last_error(ex.what());
+    return 1;
+  }
 }
 
 // ---- bookkeeping -------------------------------------------------------------------------------------------

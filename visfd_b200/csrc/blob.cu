@@ -25,7 +25,9 @@ struct BlobCand {
 
 struct BlobScanArgs {
   const float *prev, *cur, *next, *mask;
-  int nx, ny, nz;
+  int nx, ny, nz;             // nz: planes of the slab
+  int z_offset, nz_global;    // the slab's first plane in the image, the image's planes
+  int own_z0;                 // first receiver plane (slab-local); the grid spans the receiver planes
   float min_thr, max_thr;     // device pre-filter: minima need score < min_thr, maxima > max_thr
   BlobCand *mins, *maxs;
   unsigned long long *counters;  // [0] minima, [1] maxima
@@ -50,11 +52,14 @@ __device__ __forceinline__ void append(BlobCand *list, unsigned long long *count
 __global__ void __launch_bounds__(256) blob_scan_kernel(BlobScanArgs a) {
   const int ix = blockIdx.x * 64 + (threadIdx.x & 63);
   const int iy = blockIdx.y * 4 + (threadIdx.x >> 6);
-  const int iz = blockIdx.z;
+  const int iz = a.own_z0 + blockIdx.z;
+  const int gz = a.z_offset + iz;
   bool is_min = false, is_max = false;
   float e = 0.0f;
-  // every neighbour must be inside the image (feature.hpp:245-258)
-  if (ix >= 1 && ix < a.nx - 1 && iy >= 1 && iy < a.ny - 1 && iz >= 1 && iz < a.nz - 1) {
+  // every neighbour must be inside the image (feature.hpp:245-258); the slab's halo guarantees that a
+  // neighbour inside the image is inside the slab
+  if (ix >= 1 && ix < a.nx - 1 && iy >= 1 && iy < a.ny - 1 && gz >= 1 && gz < a.nz_global - 1 && iz >= 1 &&
+      iz < a.nz - 1) {
     const size_t sy = a.nx, sz = (size_t)a.nx * a.ny;
     const size_t c = (size_t)iz * sz + (size_t)iy * sy + ix;
     e = __ldg(a.cur + c);
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(256) blob_scan_kernel(BlobScanArgs a) {
         }
     }
   }
-  BlobCand cand{(float)ix, (float)iy, (float)iz, e};
+  BlobCand cand{(float)ix, (float)iy, (float)gz, e};
   append(a.mins, a.counters + 0, a.capacity, is_min && e < a.min_thr, cand);
   append(a.maxs, a.counters + 1, a.capacity, is_max && e > a.max_thr, cand);
 }
@@ -91,12 +96,51 @@ static void sort_raster(std::vector<BlobCand> &v) {
   });
 }
 
-void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *src, const float *mask,
+// feature.hpp:362-417: the final score filter, once the best scores of the WHOLE image are known
+void blob_final_filter(BlobList &minima, BlobList &maxima, float minima_threshold, float maxima_threshold,
+                       int use_threshold_ratios, float gmin, float gmax) {
+  const float INF = std::numeric_limits<float>::infinity();
+  bool filt = (minima_threshold != INF) || (maxima_threshold != -INF);
+  bool drop_min = false, drop_max = false;
+  if (use_threshold_ratios) {
+    // An infinite RATIO admits (almost) nothing in the reference's running filter
+    // (+-inf times the running best score); the deterministic reading is an empty list.
+    if (maxima_threshold == -INF) drop_max = true;
+    if (minima_threshold == INF) drop_min = true;
+    if (filt) {
+      minima_threshold *= gmin;
+      maxima_threshold *= gmax;
+    }
+  }
+  auto keep = [&](BlobList &l, bool drop, bool is_min) {
+    BlobList out;
+    if (!drop)
+      for (size_t i = 0; i < l.score.size(); i++)
+        if (!filt || (is_min ? l.score[i] <= minima_threshold : l.score[i] >= maxima_threshold)) {
+          out.crds.insert(out.crds.end(), {l.crds[3 * i], l.crds[3 * i + 1], l.crds[3 * i + 2]});
+          out.sigma.push_back(l.sigma[i]);
+          out.score.push_back(l.score[i]);
+        }
+    l = std::move(out);
+  };
+  keep(minima, drop_min, true);
+  keep(maxima, drop_max, false);
+}
+
+// Slab form: the slab holds image planes [z_offset, z_offset + nz); candidates are produced for the
+// slab-local planes [own_z0, own_z1) with z reported as the IMAGE plane.  best[0] / best[1] receive the
+// best minimum / maximum score found (1 / -1 if none, feature.hpp:122-123).  finalize = false leaves out
+// the final filter, which needs the best scores of the whole image (blob_final_filter).
+void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, i64 z_offset, i64 nz_global, i64 own_z0, i64 own_z1,
+                     const float *src, const float *mask,
                      const float *sigmas, int n_sigmas, float delta, float truncate_ratio,
                      float minima_threshold, float maxima_threshold, int use_threshold_ratios,
-                     BlobList &minima, BlobList &maxima) {
+                     BlobList &minima, BlobList &maxima, bool finalize, float best[2]) {
   VREQUIRE(nx > 0 && ny > 0 && nz > 0, "empty volume");
-  VREQUIRE(nx < 2147483647LL / 2 && ny <= 4 * 65535LL && nz <= 65535, "volume too large for the blob scan launch");
+  VREQUIRE(z_offset >= 0 && z_offset + nz <= nz_global && 0 <= own_z0 && own_z0 <= own_z1 && own_z1 <= nz,
+           "slab / receiver planes outside the image");
+  VREQUIRE(nx < 2147483647LL / 2 && ny <= 4 * 65535LL && nz <= 65535 && nz_global < 2147483647LL,
+           "volume too large for the blob scan launch");
   const i64 N = nx * ny * nz;
   const float INF = std::numeric_limits<float>::infinity();
   Scratch<float> ring[3];
@@ -114,8 +158,11 @@ void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *src, c
     float sa[3], sb[3], scale;
     int hw[3];
     log_params(s3, delta, truncate_ratio, sa, sb, hw, &scale);
-    dog_device(ctx, nx, ny, nz, 0, nz, src, ring[ir % 3].get(), mask, sa, sb, hw, scale, nullptr, nullptr);
-    if (ir < 2) continue;
+    // an interior slab end needs hw planes for the LoG of the receiver planes' neighbours, + 1 for those
+    VREQUIRE((z_offset == 0 || own_z0 >= hw[2] + 1) && (z_offset + nz == nz_global || nz - own_z1 >= hw[2] + 1),
+             "slab lacks the halo (LoG half-width + 1 planes) around the receiver planes");
+    dog_device(ctx, nx, ny, nz, z_offset, nz_global, src, ring[ir % 3].get(), mask, sa, sb, hw, scale, nullptr, nullptr);
+    if (ir < 2 || own_z1 == own_z0) continue;
     // device pre-filter thresholds for this scale
     float min_thr = minima_threshold, max_thr = maxima_threshold;
     if (use_threshold_ratios) {
@@ -134,6 +181,7 @@ void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *src, c
       a.next = ring[ir % 3].get();
       a.mask = mask;
       a.nx = (int)nx; a.ny = (int)ny; a.nz = (int)nz;
+      a.z_offset = (int)z_offset; a.nz_global = (int)nz_global; a.own_z0 = (int)own_z0;
       a.min_thr = min_thr; a.max_thr = max_thr;
       a.mins = dmins.get(); a.maxs = dmaxs.get();
       a.counters = counters.get();
@@ -142,7 +190,7 @@ void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *src, c
       {
         StageTimer t(ctx, "blob_scan");
         VCK(cudaMemsetAsync(counters.get(), 0, 2 * sizeof(unsigned long long), ctx->stream));
-        dim3 grid(div_up(nx, 64), div_up(ny, 4), (unsigned)nz);
+        dim3 grid(div_up(nx, 64), div_up(ny, 4), (unsigned)(own_z1 - own_z0));
         blob_scan_kernel<<<grid, 256, 0, ctx->stream>>>(a);
         VCK(cudaGetLastError());
         ctx->count_launch();
@@ -168,35 +216,20 @@ void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *src, c
     }
   }
 
-  // final filter (feature.hpp:362-417)
-  bool filt = (minima_threshold != INF) || (maxima_threshold != -INF);
-  bool drop_min = false, drop_max = false;
-  if (use_threshold_ratios) {
-    // An infinite RATIO admits (almost) nothing in the reference's running filter
-    // (+-inf times the running best score); the deterministic reading is an empty list.
-    if (maxima_threshold == -INF) drop_max = true;
-    if (minima_threshold == INF) drop_min = true;
-    if (filt) {
-      minima_threshold *= gmin;
-      maxima_threshold *= gmax;
-    }
-  }
   minima = BlobList();
   maxima = BlobList();
-  if (!drop_min)
-    for (size_t i = 0; i < mins.size(); i++)
-      if (!filt || mins[i].score <= minima_threshold) {
-        minima.crds.insert(minima.crds.end(), {mins[i].x, mins[i].y, mins[i].z});
-        minima.sigma.push_back(min_sig[i]);
-        minima.score.push_back(mins[i].score);
-      }
-  if (!drop_max)
-    for (size_t i = 0; i < maxs.size(); i++)
-      if (!filt || maxs[i].score >= maxima_threshold) {
-        maxima.crds.insert(maxima.crds.end(), {maxs[i].x, maxs[i].y, maxs[i].z});
-        maxima.sigma.push_back(max_sig[i]);
-        maxima.score.push_back(maxs[i].score);
-      }
+  for (size_t i = 0; i < mins.size(); i++) {
+    minima.crds.insert(minima.crds.end(), {mins[i].x, mins[i].y, mins[i].z});
+    minima.sigma.push_back(min_sig[i]);
+    minima.score.push_back(mins[i].score);
+  }
+  for (size_t i = 0; i < maxs.size(); i++) {
+    maxima.crds.insert(maxima.crds.end(), {maxs[i].x, maxs[i].y, maxs[i].z});
+    maxima.sigma.push_back(max_sig[i]);
+    maxima.score.push_back(maxs[i].score);
+  }
+  if (best) { best[0] = gmin; best[1] = gmax; }
+  if (finalize) blob_final_filter(minima, maxima, minima_threshold, maxima_threshold, use_threshold_ratios, gmin, gmax);
 }
 
 }  // namespace visfd_cuda

@@ -99,10 +99,14 @@ void draw_regions_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, float *img, con
 struct BlobList {
   std::vector<float> crds, sigma, score;  // crds: 3 per entry (x,y,z)
 };
-void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *src, const float *mask,
+// slab form (whole image: z_offset 0, nz_global = nz, own planes [0, nz), finalize true); best: NULL or 2 floats
+void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, i64 z_offset, i64 nz_global, i64 own_z0, i64 own_z1,
+                     const float *src, const float *mask,
                      const float *sigmas, int n_sigmas, float delta, float truncate_ratio,
                      float minima_threshold, float maxima_threshold, int use_threshold_ratios,
-                     BlobList &minima, BlobList &maxima);
+                     BlobList &minima, BlobList &maxima, bool finalize, float best[2]);
+void blob_final_filter(BlobList &minima, BlobList &maxima, float minima_threshold, float maxima_threshold,
+                       int use_threshold_ratios, float gmin, float gmax);
 
 // ---- util.cu ----------------------------------------------------------------------
 i64 tv_count_pairs_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, const float *sal, float thr,

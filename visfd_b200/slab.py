@@ -228,3 +228,67 @@ class SlabMembrane:
             v = sm(n)
             if v >= 0:
                 self.stage_ms[n] = self.stage_ms.get(n, 0.0) + v
+
+
+# ---- scale-space blob detection over z-slabs ------------------------------------------
+def log_halfwidth(sigma, delta, truncate_ratio):
+    """Shared half-width of the two Gaussians of ApplyLog (lib/visfd/filter3d.hpp:1455-1466), with the
+    library's arithmetic (log_params, gauss.cu): the wider sigma in double, rounded to float, times the
+    float ratio."""
+    s_b = np.float32(np.float64(np.float32(sigma)) * (1.0 + 0.5 * np.float64(np.float32(delta))))
+    return int(np.floor(np.float32(truncate_ratio) * s_b))
+
+
+class SlabBlobs:
+    """BlobDog (lib/visfd/feature.hpp:56-427) on this rank's z-slab.  Halo = largest LoG half-width + 1
+    planes of raw source (fetched like the membrane pipeline's); every rank scans its own planes; the
+    candidate lists are all-gathered and concatenated per scale in rank (= z) order, which is the
+    reference's (scale, z, y, x) order; the best scores are all-reduced (min / max) before the final
+    ratio filter (feature.hpp:341-344, :369-372)."""
+
+    def __init__(self, backend, shape, sigmas, delta=0.02, truncate_ratio=2.5, rank=0, world=1, dist=None,
+                 device=None):
+        self.backend, self.dist, self.device = backend, dist, device
+        self.nz, self.ny, self.nx = shape
+        self.sigmas = np.ascontiguousarray(np.asarray(sigmas), np.float32)
+        self.delta, self.truncate_ratio = delta, truncate_ratio
+        hw = max(log_halfwidth(s, delta, truncate_ratio) for s in self.sigmas)
+        # make_plan's halo is tv_hw + 1 + gauss_hw: (hw, tv 0) gives hw + 1
+        self.plan = make_plan(self.nz, world, rank, hw, 0)
+        self.slab_src = None
+
+    def run(self, own_src, minima_threshold=np.inf, maxima_threshold=-np.inf, use_threshold_ratios=True,
+            capacity=1 << 20):
+        import torch
+        plan, be = self.plan, self.backend
+        if plan.world == 1:
+            src = own_src
+        else:
+            if self.slab_src is None:
+                self.slab_src = torch.empty((plan.slab[1] - plan.slab[0], self.ny, self.nx), dtype=torch.float32,
+                                            device=self.device)
+            exchange_halo(plan, own_src, self.slab_src, self.dist)
+            src = self.slab_src
+        kw = dict(minima_threshold=minima_threshold, maxima_threshold=maxima_threshold,
+                  use_threshold_ratios=use_threshold_ratios)
+        mins, maxs, best = be.blob_dog_slab(src, plan.slab[0], self.nz, plan.own_local, self.sigmas, self.delta,
+                                            self.truncate_ratio, capacity=capacity, **kw)
+        if plan.world > 1:
+            parts = [None] * plan.world
+            self.dist.all_gather_object(parts, (mins, maxs))
+            t = torch.tensor([best[0], -best[1]], dtype=torch.float32, device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+            best = (float(t[0].item()), -float(t[1].item()))
+            mins = _concat_by_scale([p[0] for p in parts], self.sigmas)
+            maxs = _concat_by_scale([p[1] for p in parts], self.sigmas)
+        return be.blob_finalize(mins, maxs, best, **kw)
+
+
+def _concat_by_scale(lists, sigmas):
+    """Per scale (in the order of `sigmas`), the ranks' rows in rank order."""
+    out = []
+    for s in sigmas:
+        for rows in lists:
+            rows = np.asarray(rows, np.float32).reshape(-1, 5)
+            out.append(rows[rows[:, 3] == np.float32(s)])
+    return np.concatenate(out, axis=0) if out else np.zeros((0, 5), np.float32)
