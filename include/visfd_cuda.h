@@ -287,6 +287,12 @@ int visfd_cuda_threshold(visfd_ctx *ctx, int64_t n_voxels, const float *in, floa
 /* AverageArr / StdDevArr (lib/visfd/visfd_utils.hpp:685-790), needed by -cl. */
 int visfd_cuda_mean_stddev(visfd_ctx *ctx, int64_t n_voxels, const float *in,
                            const float *weights, float *mean_out, float *stddev_out);
+/* The two sums behind them, for a multi-GPU caller ("-cl needs mean + stddev => allreduce"):
+ * sums[0] = sum w*h, or sum w*(h - center)^2 when squared != 0; sums[1] = sum w (w = 1 without
+ * weights); both in double.  All-reduce (sum) over the ranks, then mean = s0/s1 and, after a second
+ * call with center = (float)mean, stddev = sqrt(s0/s1). */
+int visfd_cuda_moment_sums(visfd_ctx *ctx, int64_t n_voxels, const float *in, const float *weights,
+                           double center, int squared, double sums[2]);
 
 /* ---- binning (the resampling filter_mrc wraps around the path) ------ */
 /* BinArray3D<float,int>: lib/visfd/resample.hpp:53-104 (caller HandleBinning,

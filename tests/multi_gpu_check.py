@@ -83,6 +83,16 @@ def main():
             print(f"blobs ({'ratio' if kw['use_threshold_ratios'] else 'absolute'} thresholds): world {world}, shape {bshape}, "
                   f"{len(want[0])} minima, {len(want[1])} maxima: {'identical' if same else 'DIFFERENT'}", flush=True)
             ok = ok and same and len(want[0]) > 0
+    # ---- mean / standard deviation of the whole image from per-rank sums (-cl) ----------------------------
+    from visfd_b200.slab import distributed_mean_stddev
+    own = torch.from_numpy(bvol[o0:o1]).to(dev)
+    mean, std = distributed_mean_stddev(ctx, own, None, dist=dist, world=world, device=dev)
+    if rank == 0:
+        m1, s1 = ctx.mean_stddev(torch.from_numpy(bvol).to(dev))
+        same = abs(mean - m1) <= 1e-6 * abs(m1) + 1e-9 and abs(std - s1) <= 1e-6 * s1
+        print(f"mean/stddev over {world} ranks: {mean:.7g} {std:.7g} (one GPU {m1:.7g} {s1:.7g}): "
+              f"{'equal' if same else 'DIFFERENT'}", flush=True)
+        ok = ok and same
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()

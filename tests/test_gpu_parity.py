@@ -472,6 +472,27 @@ def test_mean_stddev(ctx, golden):
     m, s = ctx.mean_stddev(vol)
     mw, sw = ctx.mean_stddev(vol, mask)
     np.testing.assert_allclose([m, s, mw, sw], golden["mean_std"], rtol=2e-6)
+    # the same numbers from per-slab partial sums (what the ranks all-reduce for -cl)
+    import torch
+    from visfd_b200.slab import distributed_mean_stddev, partition
+
+    class TwoRanks:                      # stands in for torch.distributed: sums over two emulated ranks
+        def __init__(self, parts):
+            self.parts, self.calls = parts, 0
+
+        def moment_sums(self, own, w, center, squared):
+            tot = [0.0, 0.0]
+            for a, ww in self.parts:
+                s = ctx.moment_sums(a, ww, center, squared)
+                tot = [tot[0] + s[0], tot[1] + s[1]]
+            return tuple(tot)
+
+    (a0, a1), (b0, b1) = partition(vol.shape[0], 2)
+    dv, dm = torch.from_numpy(vol).cuda(), torch.from_numpy(mask).cuda()
+    be = TwoRanks([(dv[a0:a1].contiguous(), None), (dv[b0:b1].contiguous(), None)])
+    assert distributed_mean_stddev(be, None) == (m, s)
+    be = TwoRanks([(dv[a0:a1].contiguous(), dm[a0:a1].contiguous()), (dv[b0:b1].contiguous(), dm[b0:b1].contiguous())])
+    np.testing.assert_allclose(distributed_mean_stddev(be, None), (mw, sw), rtol=1e-6)
 
 
 # ---- blobs ---------------------------------------------------------------------------------------------------

@@ -433,6 +433,14 @@ class Context:
                                                _f(0.0 if masked_value is None else masked_value)))
         return res
 
+    def moment_sums(self, a, weights=None, center=0.0, squared=False):
+        """visfd_cuda_moment_sums -> (sum w*h or sum w*(h-center)^2, sum w) as Python floats (double)."""
+        a, weights = _prep(a), _prep(weights)
+        n = a.numel() if _is_torch(a) else a.size
+        out = (_d * 2)()
+        self._ck(self.lib.visfd_cuda_moment_sums(self.h, _i64(n), _ptr(a), _ptr(weights), _d(center), _i(int(squared)), out))
+        return out[0], out[1]
+
     def mean_stddev(self, a, weights=None):
         a, weights = _prep(a), _prep(weights)
         n = a.numel() if _is_torch(a) else a.size

@@ -504,6 +504,16 @@ int visfd_cuda_draw_regions(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, 
   API_END(ctx)
 }
 
+int visfd_cuda_moment_sums(visfd_ctx *ctx, int64_t n, const float *in, const float *weights, double center,
+                           int squared, double sums[2]) {
+  API_BEGIN(ctx)
+  VREQUIRE(n >= 0 && (in || n == 0) && sums, "bad arguments");
+  const bool host = on_host(in);
+  Staged<float> i(ctx, in, n, Dir::In, host), w(ctx, weights, n, Dir::In, host);
+  moment_sums_device(ctx, n, i.get(), w.get(), center, squared != 0, sums);
+  API_END(ctx)
+}
+
 int visfd_cuda_mean_stddev(visfd_ctx *ctx, int64_t n, const float *in, const float *weights, float *mean_out,
                            float *stddev_out) {
   API_BEGIN(ctx)

@@ -82,6 +82,8 @@ void threshold_device(visfd_ctx *ctx, i64 n, const float *in, float *out, int ki
                       int use_masked_value, float masked_value);
 void mean_stddev_device(visfd_ctx *ctx, i64 n, const float *in, const float *w, float *mean,
                         float *stddev);
+void moment_sums_device(visfd_ctx *ctx, i64 n, const float *in, const float *w, double center, bool squared,
+                        double sums[2]);
 
 // ---- resample.cu ------------------------------------------------------------------
 // BinArray3D / UnbinArray3D (lib/visfd/resample.hpp:53-166); sizes are {nx, ny, nz}.

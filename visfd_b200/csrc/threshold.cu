@@ -127,34 +127,34 @@ moments_kernel(const float *__restrict__ in, const float *__restrict__ w, i64 n,
 // denominator saturates at 2^24 voxels); the device reduction is in double, i.e. it
 // agrees with the reference to float rounding on small volumes and is deliberately
 // the exact value on large ones.
-void mean_stddev_device(visfd_ctx *ctx, i64 n, const float *in, const float *w, float *mean,
-                        float *stddev) {
-  VREQUIRE(n > 0, "mean/stddev of an empty volume");
+// sums[0] = sum w*h (squared: sum w*(h-center)^2), sums[1] = sum w (w = 1 without weights), in double
+void moment_sums_device(visfd_ctx *ctx, i64 n, const float *in, const float *w, double center, bool squared,
+                        double sums[2]) {
+  VREQUIRE(n >= 0, "negative length");
+  sums[0] = sums[1] = 0.0;
+  if (n == 0) return;
   Scratch<double> d(ctx, 2);
   int grid = (int)std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16);
-  double h[2];
-  float ave;
   {
     StageTimer timer(ctx, "threshold");
     VCK(cudaMemsetAsync(d.get(), 0, 2 * sizeof(double), ctx->stream));
-    moments_kernel<<<grid, 256, 0, ctx->stream>>>(in, w, n, 0.0, 0, d.get());
+    moments_kernel<<<grid, 256, 0, ctx->stream>>>(in, w, n, center, squared ? 1 : 0, d.get());
     VCK(cudaGetLastError());
     ctx->count_launch();
   }
-  VCK(cudaMemcpyAsync(h, d.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  VCK(cudaMemcpyAsync(sums, d.get(), 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   VCK(cudaStreamSynchronize(ctx->stream));
-  ave = (float)(h[0] / h[1]);
+}
+
+void mean_stddev_device(visfd_ctx *ctx, i64 n, const float *in, const float *w, float *mean,
+                        float *stddev) {
+  VREQUIRE(n > 0, "mean/stddev of an empty volume");
+  double h[2];
+  moment_sums_device(ctx, n, in, w, 0.0, false, h);
+  const float ave = (float)(h[0] / h[1]);
   if (mean) *mean = ave;
   if (stddev) {
-    {
-      StageTimer timer(ctx, "threshold");
-      VCK(cudaMemsetAsync(d.get(), 0, 2 * sizeof(double), ctx->stream));
-      moments_kernel<<<grid, 256, 0, ctx->stream>>>(in, w, n, (double)ave, 1, d.get());
-      VCK(cudaGetLastError());
-      ctx->count_launch();
-    }
-    VCK(cudaMemcpyAsync(h, d.get(), sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    VCK(cudaStreamSynchronize(ctx->stream));
+    moment_sums_device(ctx, n, in, w, (double)ave, true, h);
     *stddev = (float)sqrt(h[0] / h[1]);
   }
 }

@@ -137,6 +137,26 @@ def distributed_cut_threshold(backend, saliency_own, fraction, mask_own=None, di
     return backend.key_to_float(prefix)
 
 
+def distributed_mean_stddev(backend, own, weights_own=None, dist=None, world=1, device=None):
+    """AverageArr / StdDevArr (lib/visfd/visfd_utils.hpp:685-790) of a volume spread over the ranks: two
+    all-reduces of (sum, weight) pairs in double.  Needed by `-cl` (SelectIntensityRangeGauss,
+    lib/threshold/threshold.hpp:248-258), whose mean and standard deviation are those of the whole image."""
+    import torch
+
+    def reduced(center, squared):
+        s = backend.moment_sums(own, weights_own, center, squared)
+        if world > 1:
+            t = torch.tensor(s, dtype=torch.float64, device=device)
+            dist.all_reduce(t)
+            s = (float(t[0].item()), float(t[1].item()))
+        return s
+
+    s0, s1 = reduced(0.0, False)
+    mean = float(np.float32(s0 / s1))
+    q0, q1 = reduced(mean, True)
+    return mean, float(np.float32(np.sqrt(q0 / q1)))
+
+
 class _Trace:
     """VISFD_SLAB_TRACE=1: wall-clock per phase of SlabMembrane.run (with device syncs), to stderr."""
 
