@@ -39,6 +39,22 @@ __device__ __forceinline__ void hist_add(unsigned int *sh, bool valid, uint32_t 
   }
 }
 
+// One key into the CTA's histogram.  Saliencies cluster in a few bins of the first pass, so lanes of
+// a warp that hold the same bin as lane 0 are counted with one atomic (the common long runs: zeros,
+// one exponent), the others individually.
+__device__ __forceinline__ void hist_add4(unsigned int *sh, const bool valid[4], const uint32_t bin[4]) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const uint32_t b0 = __shfl_sync(full, bin[e], 0);
+    const unsigned same = __ballot_sync(full, valid[e] && bin[e] == b0);
+    if ((threadIdx.x & 31) == 0 && same) atomicAdd(&sh[b0], (unsigned)__popc(same));
+    if (valid[e] && bin[e] != b0) atomicAdd(&sh[bin[e]], 1u);
+  }
+}
+
+// Four consecutive voxels per thread and iteration (one 16-byte load; the ragged tail and unaligned
+// volumes go through the scalar path of the last iterations).
 __global__ void __launch_bounds__(512)
 select_hist_kernel(const float *__restrict__ sal, const float *__restrict__ mask, i64 n,
                    uint32_t prefix, int prefix_bits, int bin_bits,
@@ -48,16 +64,41 @@ select_hist_kernel(const float *__restrict__ sal, const float *__restrict__ mask
   __syncthreads();
   const int shift = 32 - prefix_bits - bin_bits;
   const uint32_t bin_mask = (1u << bin_bits) - 1u;
+  const int pshift = 32 - prefix_bits;            // 32 when there is no prefix yet (never shifted by)
+  const bool vec = ((reinterpret_cast<uintptr_t>(sal) | (mask ? reinterpret_cast<uintptr_t>(mask) : 0)) & 15) == 0;
+  const i64 n4 = vec ? n / 4 : 0;                 // float4 groups
   const i64 stride = (i64)gridDim.x * blockDim.x;
-  // the loop bound is warp-uniform so that hist_add's warp collectives are safe
-  const i64 n_round = (n + 31) & ~(i64)31;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    bool valid = i < n;
+  // loop bounds are warp-uniform so that the warp collectives are safe
+  const i64 n4_round = (n4 + 31) & ~(i64)31;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n4_round; i += stride) {
+    bool valid[4] = {false, false, false, false};
+    uint32_t bin[4] = {0, 0, 0, 0};
+    if (i < n4) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(sal) + i);
+      const uint32_t key[4] = {key_of_bits(__float_as_uint(v.x)), key_of_bits(__float_as_uint(v.y)),
+                               key_of_bits(__float_as_uint(v.z)), key_of_bits(__float_as_uint(v.w))};
+      float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (mask) m = __ldg(reinterpret_cast<const float4 *>(mask) + i);
+      const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        valid[e] = mm[e] != 0.0f && (prefix_bits == 0 || (key[e] >> pshift) == prefix);
+        bin[e] = (key[e] >> shift) & bin_mask;
+      }
+    }
+    // later passes: almost nothing matches the prefix any more
+    if (!__any_sync(0xffffffffu, valid[0] || valid[1] || valid[2] || valid[3])) continue;
+    hist_add4(sh, valid, bin);
+  }
+  const i64 tail0 = n4 * 4, n_tail = n - tail0;
+  const i64 tail_round = (n_tail + 31) & ~(i64)31;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < tail_round; i += stride) {
+    bool valid = i < n_tail;
     uint32_t key = 0;
     if (valid) {
-      key = key_of_bits(__float_as_uint(__ldg(sal + i)));
-      if (mask && __ldg(mask + i) == 0.0f) valid = false;
-      if (prefix_bits > 0 && (key >> (32 - prefix_bits)) != prefix) valid = false;
+      key = key_of_bits(__float_as_uint(__ldg(sal + tail0 + i)));
+      if (mask && __ldg(mask + tail0 + i) == 0.0f) valid = false;
+      if (prefix_bits > 0 && (key >> pshift) != prefix) valid = false;
     }
     hist_add(sh, valid, (key >> shift) & bin_mask);
   }

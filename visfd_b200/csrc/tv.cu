@@ -118,15 +118,50 @@ __device__ __forceinline__ bool is_voter(const VoterSrc &v, int x, int y, i64 z,
   return true;
 }
 
-// one CTA (512 threads) per brick
-__global__ void __launch_bounds__(BR3) voter_count_kernel(VoterSrc v, uint32_t *__restrict__ counts) {
-  const int b = blockIdx.x;
-  const int bx = b % v.nbx, by = (b / v.nbx) % v.nby, bz = b / (v.nbx * v.nby);
+// One CTA (512 threads = one thread per voxel of a brick) per run of VB consecutive bricks: the VB loads of
+// a thread are independent, so a CTA has VB times the bytes in flight of a one-brick CTA (which spent its
+// life waiting for a single load), and consecutive bricks are neighbours in x: 256-byte rows per warp.
+constexpr int VB = 8;
+
+struct BrickPos {
+  int bx, by, bz;
+};
+__device__ __forceinline__ BrickPos brick_pos(const VoterSrc &v, i64 b) {
+  BrickPos p;
+  p.bx = (int)(b % v.nbx);
+  const i64 r = b / v.nbx;
+  p.by = (int)(r % v.nby);
+  p.bz = (int)(r / v.nby);
+  return p;
+}
+__device__ __forceinline__ void next_brick(const VoterSrc &v, BrickPos &p) {
+  if (++p.bx == v.nbx) {
+    p.bx = 0;
+    if (++p.by == v.nby) { p.by = 0; p.bz++; }
+  }
+}
+
+__global__ void __launch_bounds__(BR3) voter_count_kernel(VoterSrc v, i64 n_bricks, uint32_t *__restrict__ counts) {
+  __shared__ uint32_t cnt[VB];
   const int t = threadIdx.x;
-  float w;
-  bool p = is_voter(v, bx * BR + (t & 7), by * BR + ((t >> 3) & 7), (i64)bz * BR + (t >> 6), w);
-  int c = __syncthreads_count(p);
-  if (t == 0) counts[b] = (uint32_t)c;
+  if (t < VB) cnt[t] = 0;
+  __syncthreads();
+  const i64 b0 = (i64)blockIdx.x * VB;
+  BrickPos bp = brick_pos(v, b0);
+  bool p[VB];
+#pragma unroll
+  for (int k = 0; k < VB; k++) {
+    float w;
+    p[k] = (b0 + k < n_bricks) && is_voter(v, bp.bx * BR + (t & 7), bp.by * BR + ((t >> 3) & 7), (i64)bp.bz * BR + (t >> 6), w);
+    next_brick(v, bp);
+  }
+#pragma unroll
+  for (int k = 0; k < VB; k++) {
+    const unsigned bal = __ballot_sync(0xffffffffu, p[k]);
+    if ((t & 31) == 0 && bal) atomicAdd(&cnt[k], (uint32_t)__popc(bal));
+  }
+  __syncthreads();
+  if (t < VB && b0 + t < n_bricks) counts[b0 + t] = cnt[t];
 }
 
 // Exclusive scan of n uint32 counters into off[0..n] (off[n] = total): per-block scan,
@@ -254,34 +289,51 @@ __device__ __forceinline__ void voter_direction(const DirSrc &d, int nx, int ny,
   n[2] = (float)e0[2];
 }
 
-// Pass 1 of the fill (one CTA per brick): positions and weights in brick order.
-__global__ void __launch_bounds__(BR3)
-voter_fill_kernel(VoterSrc v, const uint32_t *__restrict__ off, float inv_total,
+// Pass 1 of the fill (one CTA per run of VB bricks): positions and weights in brick order, voxels of a
+// brick in thread order (z, y, x).
+__global__ void __launch_bounds__(BR3, 2)
+voter_fill_kernel(VoterSrc v, i64 n_bricks, const uint32_t *__restrict__ off, float inv_total,
                   VoterRec *__restrict__ rec, uint32_t *__restrict__ nonpos_flag) {
-  __shared__ uint32_t wsum[BR3 / 32];
-  const int b = blockIdx.x;
-  const uint32_t o0 = off[b], o1 = off[b + 1];
-  if (o0 == o1) return;  // uniform per CTA
-  const int bx = b % v.nbx, by = (b / v.nbx) % v.nby, bz = b / (v.nbx * v.nby);
+  __shared__ uint32_t wsum[VB][BR3 / 32];
+  const i64 b0 = (i64)blockIdx.x * VB;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int x = bx * BR + (t & 7), y = by * BR + ((t >> 3) & 7);
-  const i64 z = (i64)bz * BR + (t >> 6);
-  float wt = 0.0f;
-  bool p = is_voter(v, x, y, z, wt);
-  unsigned bal = __ballot_sync(0xffffffffu, p);
-  if (lane == 0) wsum[w] = __popc(bal);
+  const int nb = (int)min((i64)VB, n_bricks - b0);
+  if (off[b0] == off[b0 + nb]) return;  // uniform per CTA: no voter in any of its bricks
+  const int tx = t & 7, ty = (t >> 3) & 7, tz = t >> 6;
+  BrickPos bp = brick_pos(v, b0);
+  unsigned mine = 0;   // bit k: this thread's voxel of brick k votes
+  float wt[VB];
+#pragma unroll
+  for (int k = 0; k < VB; k++) {
+    wt[k] = 0.0f;
+    if (k < nb && is_voter(v, bp.bx * BR + tx, bp.by * BR + ty, (i64)bp.bz * BR + tz, wt[k])) mine |= 1u << k;
+    next_brick(v, bp);
+  }
+  unsigned bal[VB];
+#pragma unroll
+  for (int k = 0; k < VB; k++) {
+    bal[k] = __ballot_sync(0xffffffffu, (mine >> k) & 1u);
+    if (lane == 0) wsum[k][w] = __popc(bal[k]);
+  }
   __syncthreads();
-  if (!p) return;
-  uint32_t rank = __popc(bal & ((1u << lane) - 1u));
-  for (int k = 0; k < w; k++) rank += wsum[k];
-  const float wgt = wt * inv_total;
-  if (!(wgt > 0.0f)) *nonpos_flag = 1u;  // benign race: every writer stores the same value
-  // the three forms of the weight the gather kernels fold into their arithmetic (vote())
-  const float w4 = 4.0f * wgt, l4 = log2f(w4);
-  VoterRec *r = rec + o0 + rank;
-  r->a = make_float4(-(float)x, -(float)y, -(float)z, 0.5f * l4);
-  r->b.w = l4;
-  r->c.w = w4;
+  if (!mine) return;
+  bp = brick_pos(v, b0);
+#pragma unroll
+  for (int k = 0; k < VB; k++) {
+    if ((mine >> k) & 1u) {
+      uint32_t rank = __popc(bal[k] & ((1u << lane) - 1u));
+      for (int q = 0; q < w; q++) rank += wsum[k][q];
+      const float wgt = wt[k] * inv_total;
+      if (!(wgt > 0.0f)) *nonpos_flag = 1u;  // benign race: every writer stores the same value
+      // the three forms of the weight the gather kernels fold into their arithmetic (vote())
+      const float w4 = 4.0f * wgt, l4 = log2f(w4);
+      VoterRec *r = rec + off[b0 + k] + rank;
+      r->a = make_float4(-(float)(bp.bx * BR + tx), -(float)(bp.by * BR + ty), -(float)(bp.bz * BR + tz), 0.5f * l4);
+      r->b.w = l4;
+      r->c.w = w4;
+    }
+    next_brick(v, bp);
+  }
 }
 
 // Pass 2: one THREAD per voter (dense lanes -- in the brick pass only ~5 % of the lanes are
@@ -721,7 +773,7 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   Scratch<VoterRec> rec;
   {
     StageTimer t(ctx, "compact");
-    voter_count_kernel<<<(unsigned)n_bricks, BR3, 0, ctx->stream>>>(vs, counts.get());
+    voter_count_kernel<<<(unsigned)div_up(n_bricks, VB), BR3, 0, ctx->stream>>>(vs, n_bricks, counts.get());
     VCK(cudaGetLastError());
     scan_local_kernel<<<(unsigned)n_scan_blocks, SCAN_T, 0, ctx->stream>>>(counts.get(), off.get(), sums.get(), n_bricks);
     VCK(cudaGetLastError());
@@ -738,8 +790,8 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
     if (n_voters > 0) {
       DirSrc ds{direction, smoothed, ridge_sigma, eival_order, z_offset, nz_global};
       VCK(cudaMemsetAsync(sums.get() + n_scan_blocks + 1, 0, sizeof(uint32_t), ctx->stream));
-      voter_fill_kernel<<<(unsigned)n_bricks, BR3, 0, ctx->stream>>>(vs, off.get(), 1.0f / info.total, rec.get(),
-                                                                     sums.get() + n_scan_blocks + 1);
+      voter_fill_kernel<<<(unsigned)div_up(n_bricks, VB), BR3, 0, ctx->stream>>>(vs, n_bricks, off.get(), 1.0f / info.total,
+                                                                                 rec.get(), sums.get() + n_scan_blocks + 1);
       VCK(cudaGetLastError());
       voter_direction_kernel<<<div_up(n_voters, 256), 256, 0, ctx->stream>>>(ds, (int)nx, (int)ny, n_voters, rec.get());
       VCK(cudaGetLastError());
