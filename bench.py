@@ -52,7 +52,7 @@ CPU_SAMPLE = (128, 128, 128)
 # `ncu --set full` capture of the named workload (profiles/r01_tv_gather_ncu_full.csv)
 # ("C4": a metrics-only ncu pass of `bench.py --steps 1 --warmup 0`: the 10.3 GB voter list is
 # re-read once per layer of receiver tiles it serves; 10.7 GB/s, nowhere near the HBM roofline)
-NCU_TRAFFIC_BYTES = {"dev": 41.19e6 + 24.87e6, "C4": 72.06e9 + 17.45e9}
+NCU_TRAFFIC_BYTES = {"dev": 42.21e6 + 21.52e6, "C4": 72.06e9 + 17.45e9}
 
 
 def parse():
