@@ -49,43 +49,156 @@ __device__ __forceinline__ void append(BlobCand *list, unsigned long long *count
   }
 }
 
-__global__ void __launch_bounds__(256) blob_scan_kernel(BlobScanArgs a) {
-  const int ix = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int iy = blockIdx.y * 4 + (threadIdx.x >> 6);
-  const int iz = a.own_z0 + blockIdx.z;
-  const int gz = a.z_offset + iz;
-  bool is_min = false, is_max = false;
-  float e = 0.0f;
-  // every neighbour must be inside the image (feature.hpp:245-258); the slab's halo guarantees that a
-  // neighbour inside the image is inside the slab
-  if (ix >= 1 && ix < a.nx - 1 && iy >= 1 && iy < a.ny - 1 && gz >= 1 && gz < a.nz_global - 1 && iz >= 1 &&
-      iz < a.nz - 1) {
-    const size_t sy = a.nx, sz = (size_t)a.nx * a.ny;
-    const size_t c = (size_t)iz * sz + (size_t)iy * sy + ix;
-    e = __ldg(a.cur + c);
-    is_min = e < 0.0f;   // minima need score < 0, maxima score > 0 (:270-271, :289-290)
-    is_max = e > 0.0f;
-    if (a.mask && __ldg(a.mask + c) == 0.0f) is_min = is_max = false;
-    const float *vol[3] = {a.cur, a.prev, a.next};
-    for (int r = 0; r < 3 && (is_min || is_max); r++) {
-      const float *v = vol[r];
-      for (int jz = -1; jz <= 1 && (is_min || is_max); jz++)
-        for (int jy = -1; jy <= 1; jy++) {
-          const size_t row = c + jz * (ptrdiff_t)sz + jy * (ptrdiff_t)sy;
+// A warp owns 32 consecutive x of one y and marches through BLOB_ZC planes.
+// Phase A -- the 26 neighbours of the voxel's own scale.  The warp keeps the rows y-1, y, y+1 of the planes
+// z-1, z, z+1 in registers (own column per lane; the x-1 / x+1 columns come from the neighbouring lanes by
+// shuffle, lanes 0 and 31 load theirs); stepping to the next plane loads three rows, and they are
+// requested one plane ahead, so the latency of the kernel's only compulsory traffic (4 B/voxel) is hidden
+// behind the comparisons of the plane before.  A strict extremum of its own scale survives.
+// Phase B -- survivors are queued in shared memory and, 32 at a time, tested against their 27 + 27
+// neighbours in the scales below and above by the WHOLE warp (lane = neighbour, four survivors in
+// flight), instead of every voxel's lane walking 54 dependent loads while its 31 neighbours wait.
+constexpr int BLOB_ZC = 16;
+
+struct BlobPending {
+  unsigned long long at;   // linear index of the voxel in the slab
+  float e;
+  int x, gz;
+  int flags;               // 1 minimum candidate, 2 maximum candidate
+};
+
+__device__ __forceinline__ void blob_flush(const BlobScanArgs &a, BlobPending *q, int n, int iy) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const size_t sy = a.nx, sz = (size_t)a.nx * a.ny;
+  const ptrdiff_t off = (lane < 27) ? (lane / 9 - 1) * (ptrdiff_t)sz + ((lane / 3) % 3 - 1) * (ptrdiff_t)sy + (lane % 3 - 1) : 0;
+  bool my_min = false, my_max = false;
+  for (int j0 = 0; j0 < n; j0 += 4) {
+    float p[4], nx_[4], es[4];
 #pragma unroll
-          for (int jx = -1; jx <= 1; jx++) {
-            if (r == 0 && jx == 0 && jy == 0 && jz == 0) continue;
-            float nb = __ldg(v + row + jx);
-            if (nb <= e) is_min = false;
-            if (nb >= e) is_max = false;
-            if (r == 0 && a.mask && __ldg(a.mask + row + jx) == 0.0f) is_min = is_max = false;
-          }
-        }
+    for (int u = 0; u < 4; u++) {
+      const int j = min(j0 + u, n - 1);
+      es[u] = q[j].e;
+      const size_t at = (size_t)q[j].at + off;
+      p[u] = (lane < 27) ? __ldg(a.prev + at) : 0.0f;
+      nx_[u] = (lane < 27) ? __ldg(a.next + at) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      // the reference's tests (feature.hpp:245-258): nb <= e spoils a minimum, nb >= e a maximum
+      const bool ok_min = __all_sync(full, lane >= 27 || (!(p[u] <= es[u]) && !(nx_[u] <= es[u])));
+      const bool ok_max = __all_sync(full, lane >= 27 || (!(p[u] >= es[u]) && !(nx_[u] >= es[u])));
+      if (lane == j0 + u) { my_min = ok_min; my_max = ok_max; }
     }
   }
-  BlobCand cand{(float)ix, (float)iy, (float)gz, e};
-  append(a.mins, a.counters + 0, a.capacity, is_min && e < a.min_thr, cand);
-  append(a.maxs, a.counters + 1, a.capacity, is_max && e > a.max_thr, cand);
+  const bool mine = lane < n;
+  BlobCand cand{0.f, 0.f, 0.f, 0.f};
+  int flags = 0;
+  if (mine) {
+    cand = BlobCand{(float)q[lane].x, (float)iy, (float)q[lane].gz, q[lane].e};
+    flags = q[lane].flags;
+  }
+  __syncwarp();
+  append(a.mins, a.counters + 0, a.capacity, mine && (flags & 1) && my_min && cand.score < a.min_thr, cand);
+  append(a.maxs, a.counters + 1, a.capacity, mine && (flags & 2) && my_max && cand.score > a.max_thr, cand);
+}
+
+__global__ void __launch_bounds__(256) blob_scan_kernel(BlobScanArgs a, int own_z1) {
+  __shared__ BlobPending pending[8][32];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  BlobPending *q = pending[warp];
+  const int ix = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int iy = blockIdx.y * 4 + (threadIdx.x >> 6);
+  // every neighbour must be inside the image (feature.hpp:245-258); the slab's halo guarantees that a
+  // neighbour inside the image is inside the slab.  Row conditions are uniform over the warp.
+  if (iy < 1 || iy >= a.ny - 1) return;
+  const int z_begin = a.own_z0 + blockIdx.z * BLOB_ZC, z_end = min(z_begin + BLOB_ZC, own_z1);
+  const size_t sy = a.nx, sz = (size_t)a.nx * a.ny;
+  const bool in_x = ix < a.nx, interior = ix >= 1 && ix < a.nx - 1;
+  const bool left = lane == 0 && interior, right = lane == 31 && interior;
+  const size_t col = (size_t)iy * sy + ix;
+
+  // rows y-1, y, y+1 of plane z (own column, and the outer columns on lanes 0 / 31); planes outside the
+  // slab are never needed by a valid voxel
+  auto load_plane = [&](int z, float v[3], float l[3], float r[3]) {
+    const bool ok = z >= 0 && z < a.nz;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const size_t row = (size_t)max(z, 0) * sz + col + (k - 1) * (ptrdiff_t)sy;
+      v[k] = (ok && in_x) ? __ldg(a.cur + row) : 0.0f;
+      l[k] = (ok && left) ? __ldg(a.cur + row - 1) : 0.0f;
+      r[k] = (ok && right) ? __ldg(a.cur + row + 1) : 0.0f;
+    }
+  };
+  float v[3][3], l[3][3], r[3][3];   // [plane z-1, z, z+1][row]
+  load_plane(z_begin - 1, v[0], l[0], r[0]);
+  load_plane(z_begin, v[1], l[1], r[1]);
+  load_plane(z_begin + 1, v[2], l[2], r[2]);
+  int n_pending = 0;
+  for (int iz = z_begin; iz < z_end; iz++) {
+    float nv[3], nl[3], nr[3];
+    load_plane(iz + 2, nv, nl, nr);   // one plane ahead
+    const int gz = a.z_offset + iz;
+    const bool plane_ok = gz >= 1 && gz < a.nz_global - 1 && iz >= 1 && iz < a.nz - 1;   // uniform
+    const float e = v[1][1];
+    float nmin = __int_as_float(0x7f800000), nmax = __int_as_float(0xff800000);   // over the 26 neighbours
+#pragma unroll
+    for (int pl = 0; pl < 3; pl++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float sl = __shfl_up_sync(full, v[pl][k], 1), sr = __shfl_down_sync(full, v[pl][k], 1);
+        const float xl = (lane == 0) ? l[pl][k] : sl, xr = (lane == 31) ? r[pl][k] : sr;
+        nmin = fminf(nmin, fminf(xl, xr));
+        nmax = fmaxf(nmax, fmaxf(xl, xr));
+        if (!(pl == 1 && k == 1)) {
+          nmin = fminf(nmin, v[pl][k]);
+          nmax = fmaxf(nmax, v[pl][k]);
+        }
+      }
+    const size_t c = (size_t)iz * sz + col;
+    bool unmasked = true;
+    if (a.mask && plane_ok) {   // the voxel and its 26 neighbours must all be un-masked (feature.hpp:245-258)
+#pragma unroll
+      for (int rr = 0; rr < 9; rr++) {
+        const size_t row = c + (rr / 3 - 1) * (ptrdiff_t)sz + (rr % 3 - 1) * (ptrdiff_t)sy;
+        const bool m = in_x && __ldg(a.mask + row) != 0.0f;
+        bool ml = __shfl_up_sync(full, m, 1), mr = __shfl_down_sync(full, m, 1);
+        if (left) ml = __ldg(a.mask + row - 1) != 0.0f;
+        if (right) mr = __ldg(a.mask + row + 1) != 0.0f;
+        unmasked = unmasked && m && ml && mr;
+      }
+    }
+    // minima need score < 0, maxima score > 0 (:270-271, :289-290); strict against every neighbour
+    const bool is_min = plane_ok && interior && unmasked && e < 0.0f && e < nmin;
+    const bool is_max = plane_ok && interior && unmasked && e > 0.0f && e > nmax;
+    const unsigned alive = __ballot_sync(full, is_min || is_max);
+    const int n_new = __popc(alive);
+    if (n_pending + n_new > 32) {
+      __syncwarp();
+      blob_flush(a, q, n_pending, iy);
+      n_pending = 0;
+      __syncwarp();
+    }
+    if (is_min || is_max) {
+      BlobPending &slot = q[n_pending + __popc(alive & ((1u << lane) - 1u))];
+      slot.at = (unsigned long long)c;
+      slot.e = e;
+      slot.x = ix;
+      slot.gz = gz;
+      slot.flags = (is_min ? 1 : 0) | (is_max ? 2 : 0);
+    }
+    n_pending += n_new;
+    // roll the window
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      v[0][k] = v[1][k]; l[0][k] = l[1][k]; r[0][k] = r[1][k];
+      v[1][k] = v[2][k]; l[1][k] = l[2][k]; r[1][k] = r[2][k];
+      v[2][k] = nv[k]; l[2][k] = nl[k]; r[2][k] = nr[k];
+    }
+  }
+  __syncwarp();
+  if (n_pending) blob_flush(a, q, n_pending, iy);
 }
 
 static void sort_raster(std::vector<BlobCand> &v) {
@@ -190,8 +303,8 @@ void blob_dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz, i64 z_offset, i64 n
       {
         StageTimer t(ctx, "blob_scan");
         VCK(cudaMemsetAsync(counters.get(), 0, 2 * sizeof(unsigned long long), ctx->stream));
-        dim3 grid(div_up(nx, 64), div_up(ny, 4), (unsigned)(own_z1 - own_z0));
-        blob_scan_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+        dim3 grid(div_up(nx, 64), div_up(ny, 4), div_up(own_z1 - own_z0, BLOB_ZC));
+        blob_scan_kernel<<<grid, 256, 0, ctx->stream>>>(a, (int)own_z1);
         VCK(cudaGetLastError());
         ctx->count_launch();
       }
