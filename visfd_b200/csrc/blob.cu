@@ -2,8 +2,9 @@
 // a ring of three LoG-filtered volumes (ApplyLog per scale, gauss.cu) and, for every
 // interior scale, a strict 80-neighbour extremum test in (x,y,z,scale) that appends
 // candidates (x,y,z,score) to a device list through a warp-aggregated atomic cursor.
-// Scan traffic: the three volumes are read once from HBM (12 B/voxel); the 27-point
-// neighbourhoods come out of L1/L2.
+// Scan traffic: the three volumes are read once from HBM (12 B/voxel); the voxel's own scale
+// is held as separable row minima / maxima in registers, the two adjacent scales are only
+// touched around the extrema of the own scale.
 //
 // The reference's running score filter (:267-303) depends on OpenMP thread order; only
 // its deterministic consequences are kept: in absolute mode a candidate must beat the
@@ -103,6 +104,15 @@ __device__ __forceinline__ void blob_flush(const BlobScanArgs &a, BlobPending *q
   append(a.maxs, a.counters + 1, a.capacity, mine && (flags & 2) && my_max && cand.score > a.max_thr, cand);
 }
 
+// What a warp keeps of one plane of the voxel's own scale (rows y-1, y, y+1 of its 32 columns): the
+// minimum and maximum over x-1, x, x+1 of every row -- the separable part of the 3x3x3 test -- plus, for
+// the voxel's own row, the value itself and the minimum / maximum of its two x neighbours.
+struct BlobPlane {
+  float rmin[3], rmax[3];   // per row, over x-1..x+1
+  float pmin, pmax;         // over the three rows (the plane as the voxel's z-1 or z+1 neighbour)
+  float e, smin, smax;      // own row: centre value, min / max of the x-1 and x+1 values
+};
+
 __global__ void __launch_bounds__(256) blob_scan_kernel(BlobScanArgs a, int own_z1) {
   __shared__ BlobPending pending[8][32];
   const unsigned full = 0xffffffffu;
@@ -119,8 +129,8 @@ __global__ void __launch_bounds__(256) blob_scan_kernel(BlobScanArgs a, int own_
   const bool left = lane == 0 && interior, right = lane == 31 && interior;
   const size_t col = (size_t)iy * sy + ix;
 
-  // rows y-1, y, y+1 of plane z (own column, and the outer columns on lanes 0 / 31); planes outside the
-  // slab are never needed by a valid voxel
+  // raw rows y-1, y, y+1 of plane z (own column, and the outer columns on lanes 0 / 31); planes outside
+  // the slab are never needed by a valid voxel
   auto load_plane = [&](int z, float v[3], float l[3], float r[3]) {
     const bool ok = z >= 0 && z < a.nz;
 #pragma unroll
@@ -131,31 +141,28 @@ __global__ void __launch_bounds__(256) blob_scan_kernel(BlobScanArgs a, int own_
       r[k] = (ok && right) ? __ldg(a.cur + row + 1) : 0.0f;
     }
   };
-  float v[3][3], l[3][3], r[3][3];   // [plane z-1, z, z+1][row]
-  load_plane(z_begin - 1, v[0], l[0], r[0]);
-  load_plane(z_begin, v[1], l[1], r[1]);
-  load_plane(z_begin + 1, v[2], l[2], r[2]);
+  auto reduce_plane = [&](const float v[3], const float l[3], const float r[3], BlobPlane &p) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float sl = __shfl_up_sync(full, v[k], 1), sr = __shfl_down_sync(full, v[k], 1);
+      const float xl = (lane == 0) ? l[k] : sl, xr = (lane == 31) ? r[k] : sr;
+      const float mn = fminf(xl, xr), mx = fmaxf(xl, xr);
+      p.rmin[k] = fminf(mn, v[k]);
+      p.rmax[k] = fmaxf(mx, v[k]);
+      if (k == 1) { p.e = v[k]; p.smin = mn; p.smax = mx; }
+    }
+    p.pmin = fminf(fminf(p.rmin[0], p.rmin[1]), p.rmin[2]);
+    p.pmax = fmaxf(fmaxf(p.rmax[0], p.rmax[1]), p.rmax[2]);
+  };
+
   int n_pending = 0;
-  for (int iz = z_begin; iz < z_end; iz++) {
-    float nv[3], nl[3], nr[3];
-    load_plane(iz + 2, nv, nl, nr);   // one plane ahead
+  // the voxel of plane iz with the planes below (A), its own (B) and above (C)
+  auto test_plane = [&](int iz, const BlobPlane &A, const BlobPlane &B, const BlobPlane &C) {
     const int gz = a.z_offset + iz;
     const bool plane_ok = gz >= 1 && gz < a.nz_global - 1 && iz >= 1 && iz < a.nz - 1;   // uniform
-    const float e = v[1][1];
-    float nmin = __int_as_float(0x7f800000), nmax = __int_as_float(0xff800000);   // over the 26 neighbours
-#pragma unroll
-    for (int pl = 0; pl < 3; pl++)
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const float sl = __shfl_up_sync(full, v[pl][k], 1), sr = __shfl_down_sync(full, v[pl][k], 1);
-        const float xl = (lane == 0) ? l[pl][k] : sl, xr = (lane == 31) ? r[pl][k] : sr;
-        nmin = fminf(nmin, fminf(xl, xr));
-        nmax = fmaxf(nmax, fmaxf(xl, xr));
-        if (!(pl == 1 && k == 1)) {
-          nmin = fminf(nmin, v[pl][k]);
-          nmax = fmaxf(nmax, v[pl][k]);
-        }
-      }
+    const float e = B.e;
+    const float nmin = fminf(fminf(A.pmin, C.pmin), fminf(fminf(B.rmin[0], B.rmin[2]), B.smin));
+    const float nmax = fmaxf(fmaxf(A.pmax, C.pmax), fmaxf(fmaxf(B.rmax[0], B.rmax[2]), B.smax));
     const size_t c = (size_t)iz * sz + col;
     bool unmasked = true;
     if (a.mask && plane_ok) {   // the voxel and its 26 neighbours must all be un-masked (feature.hpp:245-258)
@@ -173,6 +180,7 @@ __global__ void __launch_bounds__(256) blob_scan_kernel(BlobScanArgs a, int own_
     const bool is_min = plane_ok && interior && unmasked && e < 0.0f && e < nmin;
     const bool is_max = plane_ok && interior && unmasked && e > 0.0f && e > nmax;
     const unsigned alive = __ballot_sync(full, is_min || is_max);
+    if (!alive) return;
     const int n_new = __popc(alive);
     if (n_pending + n_new > 32) {
       __syncwarp();
@@ -189,13 +197,29 @@ __global__ void __launch_bounds__(256) blob_scan_kernel(BlobScanArgs a, int own_
       slot.flags = (is_min ? 1 : 0) | (is_max ? 2 : 0);
     }
     n_pending += n_new;
-    // roll the window
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      v[0][k] = v[1][k]; l[0][k] = l[1][k]; r[0][k] = r[1][k];
-      v[1][k] = v[2][k]; l[1][k] = l[2][k]; r[1][k] = r[2][k];
-      v[2][k] = nv[k]; l[2][k] = nl[k]; r[2][k] = nr[k];
-    }
+  };
+
+  // three plane slots used in rotation (the loop is unrolled by three so that the roles are compile-time);
+  // the raw rows of the plane after next are in flight while a plane is tested
+  BlobPlane P0, P1, P2;
+  float v[3], l[3], r[3];
+  load_plane(z_begin - 1, v, l, r);
+  reduce_plane(v, l, r, P0);
+  load_plane(z_begin, v, l, r);
+  reduce_plane(v, l, r, P1);
+  load_plane(z_begin + 1, v, l, r);
+  for (int iz = z_begin; iz < z_end; iz += 3) {
+    reduce_plane(v, l, r, P2);          // plane iz + 1
+    load_plane(iz + 2, v, l, r);
+    test_plane(iz, P0, P1, P2);
+    if (iz + 1 >= z_end) break;
+    reduce_plane(v, l, r, P0);          // plane iz + 2
+    load_plane(iz + 3, v, l, r);
+    test_plane(iz + 1, P1, P2, P0);
+    if (iz + 2 >= z_end) break;
+    reduce_plane(v, l, r, P1);          // plane iz + 3
+    load_plane(iz + 4, v, l, r);
+    test_plane(iz + 2, P2, P0, P1);
   }
   __syncwarp();
   if (n_pending) blob_flush(a, q, n_pending, iy);
