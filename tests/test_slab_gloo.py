@@ -196,3 +196,36 @@ def test_slab_pipeline_matches_single_process(world, shape):
         got[z0:z1] = o
         assert np.float32(thr) == np.float32(want["threshold"])       # the cut is global
     assert np.array_equal(got, want["out"])
+
+
+def test_plans_cover_every_plane_once():
+    """host-only invariants of the z-slab plans for many (planes, ranks, radii): the own ranges tile
+    [0, nz) in order, rank boundaries and slab starts are multiples of 8 whenever there are 8 planes per
+    rank, a slab holds its own planes plus the halo (clipped at the image), the voter range lies inside
+    the slab, and every receive has the matching send on the other rank."""
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        world = int(rng.integers(1, 9))
+        nz = int(rng.integers(world, 700))
+        ghw, thw = int(rng.integers(0, 12)), int(rng.integers(0, 30))
+        plans = [make_plan(nz, world, r, ghw, thw) for r in range(world)]
+        halo = (thw + 1 + ghw) if thw > 0 else (1 + ghw)
+        z = 0
+        for r, p in enumerate(plans):
+            assert p.own[0] == z and p.own[1] >= p.own[0]
+            z = p.own[1]
+            assert p.halo == halo
+            assert p.slab[0] <= max(0, p.own[0] - halo) and p.slab[1] == min(nz, p.own[1] + halo)
+            assert p.slab[0] >= max(0, p.own[0] - halo - 7)
+            if nz // 8 >= world:
+                assert p.own[0] % 8 == 0 and p.slab[0] % 8 == 0
+            assert p.slab[0] <= p.vote[0] <= p.own[0] and p.own[1] <= p.vote[1] <= p.slab[1]
+            got = sorted([(a, b) for (_, a, b) in p.recvs] + ([p.own] if p.own[1] > p.own[0] else []))
+            if got:
+                assert got[0][0] == p.slab[0] or p.own[1] == p.own[0]
+                assert all(got[i][1] == got[i + 1][0] for i in range(len(got) - 1))
+            for (dst, a, b) in p.sends:
+                assert (r, a, b) in plans[dst].recvs
+            for (src, a, b) in p.recvs:
+                assert (r, a, b) in plans[src].sends
+        assert z == nz
