@@ -225,6 +225,18 @@ def main():
             subprocess.run([fm, "-w", "19.2", "-in", fixture, "-out", o2, "-membrane", "minima", "55", "-bin", "2"],
                            check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             c1n = read_mrc(o2)
+            # pass 2 of the same test (tests/test_membrane_detection.sh:9, in one invocation): the connected
+            # surfaces -- the known answer for SURVEY 8f rank 1 (LabelConnected), not yet built
+            o3 = os.path.join(td, "out_clusters.rec")
+            log = subprocess.run([fm, "-w", "19.2", "-in", fixture, "-out", o3, "-membrane", "minima", "55", "-tv", "4",
+                                  "-tv-angle-exponent", "4", "-bin", "2", "-connect", "1e+09", "-connect-angle", "30",
+                                  "-select-cluster", "1"], check=True, stdout=subprocess.DEVNULL,
+                                 stderr=subprocess.PIPE, text=True).stderr
+            c1c = read_mrc(o3)
+            n_clusters = [int(line.split()[4]) for line in log.splitlines() if "Number of clusters found:" in line]
+        out["c1_connect_labels"] = c1c
+        out["c1_connect_n_clusters"] = np.array(n_clusters, np.int64)
+        print("C1 pass 2: clusters", n_clusters, "voxels in cluster 1:", int((c1c == 1).sum()))
         # parameters exactly as settings.cpp / filter_mrc.cpp derive them (float arithmetic)
         vw = np.float32(19.2) * np.float32(2)
         sigma = np.float32(np.float32(55.0) / np.sqrt(3.0))

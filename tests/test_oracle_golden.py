@@ -212,3 +212,15 @@ def test_draw_regions_vs_reference(oracle, ref_oracle):
         for subtract in (False, True):
             eq(oracle.draw_regions(img, regions, mask=mask, negative_means_subtract=subtract),
                ref_oracle.draw_regions(img, regions, mask=mask, negative_means_subtract=subtract))
+
+
+def test_c1_pass2_known_answer(golden):
+    """tests/test_membrane_detection.sh pass 2 (-connect 1e+09 -connect-angle 30 -select-cluster 1), run by
+    the stock binary when the fixtures were made: 1 cluster of 69 voxels, all of them above the
+    saliency threshold of the post-vote image.  This pins the known answer of SURVEY 8f rank 1
+    (LabelConnected), which round 1 has not built; nothing in the product is compared here."""
+    labels, sal = golden["c1_connect_labels"], golden["c1_out"]
+    assert golden["c1_connect_n_clusters"].tolist() == [1]
+    assert labels.shape == sal.shape == (8, 8, 8)
+    assert int((labels == 1).sum()) == 69
+    assert np.all(sal[labels == 1] >= 1e9)
