@@ -218,6 +218,22 @@ class Oracle:
                                        _ptr(out))
         return dict(threshold=thr, hess_saliency=sal, direction=dire, tensor=tensor, out=out)
 
+    def label_connected(self, saliency, tensor, threshold_saliency, angle_deg=15.0, order=1, mask=None):
+        """The clustering step of HandleTV (handlers.cpp:1927-2034 -> LabelConnected, connect.hpp:171), reference
+        only: -> (labels int64, -1 undefined; number of clusters).  angle_deg as -connect-angle (settings.cpp:3075-3086)."""
+        if self.kind != "reference":
+            raise NotImplementedError("LabelConnected has no restatement yet (SURVEY 8f rank 1)")
+        sal = _f32(saliency)
+        ten = _f32(tensor)
+        mask = _f32(mask)
+        labels = np.zeros(sal.shape, np.int64)
+        c = float(np.float32(np.cos(angle_deg * np.pi / 180.0)))
+        nz, ny, nx = sal.shape
+        n = self._fn("label_connected", _i64)(_i(nx), _i(ny), _i(nz), _ptr(sal), _ptr(mask), _ptr(ten), _i(order),
+                                             _f(threshold_saliency), _f(c), _f(c), _f(c), _f(c),
+                                             labels.ctypes.data_as(C.c_void_p), None)
+        return labels, int(n)
+
     # ---- thresholds ----------------------------------------------------------
     def threshold1(self, a, thr, outA=0.0, outB=1.0):
         a = _f32(a)

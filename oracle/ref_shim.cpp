@@ -355,6 +355,49 @@ int ref_unbin3d(const int64_t size_src[3], const int64_t size_dst[3], const floa
   return 0;
 }
 
+// The clustering step of HandleTV (bin/filter_mrc/handlers.cpp:1927-2034): the first eigenvector of every
+// vote tensor becomes the voxel's direction (:1933-1950), then LabelConnected (lib/visfd/connect.hpp:171)
+// with the arguments filter_mrc passes (:1963-1993: unsigned dot products, positive-definite tensors,
+// connectivity 1, clusters sorted by size, maxima as seeds, no must-link constraints).  labels: cluster
+// id from 1 in decreasing size, -1 where undefined.  Returns the number of clusters.  SURVEY 8f rank 1:
+// the known answers for a future device implementation come from here.
+int64_t ref_label_connected(int nx, int ny, int nz, const float *saliency, const float *mask, const float *tensor,
+                            int eival_order, float threshold_saliency, float threshold_vector_saliency,
+                            float threshold_vector_neighbor, float threshold_tensor_saliency,
+                            float threshold_tensor_neighbor, int64_t *labels, float *direction_out) {
+  int size[3] = {nx, ny, nz};
+  const size_t N = size_t(nx) * ny * nz;
+  vector<Vec3> dir(N);
+  vector<float> tcopy(tensor, tensor + 6 * N);
+  vector<float *> tptr(N);
+  for (size_t i = 0; i < N; i++) {
+    tptr[i] = tcopy.data() + 6 * i;
+    float eivals[3], eivects[3][3];
+    ConvertFlatSym2Evects3(tptr[i], eivals, eivects, order_from_int(eival_order));
+    for (int d = 0; d < 3; d++) dir[i][d] = eivects[0][d];
+  }
+  vector<ptrdiff_t> lab(N);
+  View3<const float> sal(saliency, nx, ny, nz), m(mask, nx, ny, nz);
+  View3<Vec3> dtab(dir.data(), nx, ny, nz);
+  View3<float *> ttab(tptr.data(), nx, ny, nz);
+  View3<ptrdiff_t> ltab(lab.data(), nx, ny, nz);
+  vector<array<float, 3> > centers;
+  vector<float> sizes, saliencies;
+  size_t n = LabelConnected(size, sal.p, ltab.p, m.p, threshold_saliency, dtab.p, threshold_vector_saliency,
+                            threshold_vector_neighbor, false, ttab.p, threshold_tensor_saliency,
+                            threshold_tensor_neighbor, true, 1, static_cast<ptrdiff_t>(-1), &centers, &sizes,
+                            &saliencies, RegionSortCriteria::SORT_BY_SIZE, static_cast<float ***>(nullptr),
+#ifndef DISABLE_STANDARDIZE_VECTOR_DIRECTION
+                            dtab.p,
+#endif
+                            static_cast<const vector<vector<array<float, 3> > > *>(nullptr),
+                            static_cast<const vector<vector<DirectionPairType> > *>(nullptr), true,
+                            static_cast<ostream *>(nullptr));
+  for (size_t i = 0; i < N; i++) labels[i] = (int64_t)lab[i];
+  if (direction_out) memcpy(direction_out, dir.data(), 3 * N * sizeof(float));
+  return (int64_t)n;
+}
+
 // lib/visfd/draw.hpp:90-237.  regions: n records of {int32 type (0 rect, 1 sphere), float p[6],
 // float value}; rect p = xmin,xmax,ymin,ymax,zmin,zmax; sphere p = x0,y0,z0,r.
 struct RegionRecord { int32_t type; float p[6]; float value; };

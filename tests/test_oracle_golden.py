@@ -224,3 +224,16 @@ def test_c1_pass2_known_answer(golden):
     assert labels.shape == sal.shape == (8, 8, 8)
     assert int((labels == 1).sum()) == 69
     assert np.all(sal[labels == 1] >= 1e9)
+
+
+def test_label_connected_hook_reproduces_the_cli(ref_oracle, golden):
+    """oracle/ref_shim.cpp::ref_label_connected (the unmodified LabelConnected behind the arguments HandleTV
+    passes) on the C1 pipeline output == the stock binary's pass 2: test infrastructure for SURVEY 8f rank 1."""
+    sigma, ratio, tv_sigma, expo, cutoff, best = [float(v) for v in golden["c1_params"]]
+    r = ref_oracle.membrane(golden["c1_in_binned"], sigma, ratio, 1, best, True, tv_sigma, int(expo), cutoff)
+    assert np.array_equal(r["out"], golden["c1_out"])
+    labels, n = ref_oracle.label_connected(r["out"], r["tensor"], 1e9, angle_deg=30.0)
+    assert n == int(golden["c1_connect_n_clusters"][0]) == 1
+    cli = golden["c1_connect_labels"]
+    assert np.array_equal(labels == 1, cli == 1) and int((labels == 1).sum()) == 69
+    assert np.array_equal(labels == -1, cli == 2)          # undefined voxels: max label + 1 in the file
