@@ -47,7 +47,7 @@ RATIO = float(np.float32(np.sqrt(np.float32(-2) * np.log(np.float32(0.03)))))
 TV_BEST = 0.05
 WORKLOADS = {"C4": (1024, 2048, 2048), "C5": (1024, 4096, 4096), "C2": (512, 512, 512), "C3": (512, 1024, 1024),
              "dev": (256, 256, 256)}
-CPU_SAMPLE = (128, 128, 128)
+CPU_SAMPLE = tuple(int(v) for v in os.environ.get("VISFD_BENCH_CPU_SAMPLE", "128,128,128").split(","))  # override: smoke tests
 # dram__bytes_read.sum + dram__bytes_write.sum of one tv_gather_kernel launch, from the
 # `ncu --set full` capture of the named workload (profiles/r01_tv_gather_ncu_full.csv)
 # ("C4": a metrics-only ncu pass of `bench.py --steps 1 --warmup 0`: the 10.3 GB voter list is
@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--shape", default=None, help="nz,ny,nx override (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-big", action="store_true", help="reference arm: skip the extra 256^3 pass")
     return ap.parse_args()
 
 
@@ -116,42 +117,113 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(shape, seed=0):
+def host_threads():
+    """Threads the CPU arm may use: the cores this process is allowed on.  torch.distributed.run
+    exports OMP_NUM_THREADS=1 to every rank when nproc > 1, which would silently serialise the
+    reference's OpenMP loops, so the count is set explicitly on the OpenMP runtime the reference
+    library links (libgomp) after loading it."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, n)
+
+
+def _set_omp_threads(n):
+    import ctypes
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_dynamic(0)
+        gomp.omp_set_num_threads(int(n))
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return n
+
+
+def cpu_reference_run(shape, seed=0, staged=False):
     """One pass of the UNMODIFIED reference (oracle/_ref, OpenMP on all host cores) over a
-    crop of the workload; returns (seconds, cores, kind)."""
+    crop of the workload; returns (seconds, threads, kind, per-stage seconds or None).
+    staged=True calls the stages of HandleTV one by one (the same reference functions
+    ref_membrane chains: CalcHessian, eigen + score loop, cut, TVDenseStick, score loop)."""
     from oracle.pyoracle import Oracle, have
     from visfd_b200 import synth
     kind = "reference" if have("reference") else "port"
     o = Oracle(kind)
+    cores = _set_omp_threads(host_threads())
     vol = synth.tomogram(shape, seed=seed)
+    stages = None
     t = time.perf_counter()
-    o.membrane(vol, SIGMA, RATIO, 1, TV_BEST, True, TV_SIGMA, 4, SQ2, want_tensor=False)
-    return time.perf_counter() - t, os.cpu_count(), kind
+    if not staged:
+        o.membrane(vol, SIGMA, RATIO, 1, TV_BEST, True, TV_SIGMA, 4, SQ2, want_tensor=False)
+    else:
+        stages = {}
+        t0 = time.perf_counter()
+        grad, hess = o.calc_hessian(vol, SIGMA, RATIO)[:2]
+        stages["gauss_hessian"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sal, dire, _ = o.hessian_eigen_score(hess, 1, 0)
+        del hess
+        stages["eigen_score"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sal, _thr = o.saliency_cut(sal, TV_BEST, True)
+        stages["cut"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ten = o.tv_dense_stick(sal, dire, TV_SIGMA, 4, SQ2)
+        stages["tv"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        o.tensor_score(ten, 1, 0)
+        stages["post_score"] = time.perf_counter() - t0
+    return time.perf_counter() - t, cores, kind, stages
+
+
+def cpu_sample_text(shape):
+    return ("%dx%dx%d crop of the synthetic workload with the same parameters (sigma 3, vote radius 20, "
+            "tv-best 0.05): one full pipeline pass of the unmodified reference (OpenMP) per step" % tuple(shape))
 
 
 def reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path, timed on the
-    host cores on a bounded sample of the workload (a 96^3 crop with the C4 parameters)."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: the
+    unmodified lib/visfd templates behind HandleTV, handlers.cpp:1618-1892), timed on the host
+    cores on a bounded sample of the workload: a CPU_SAMPLE crop with the C4 parameters per step.
+    The reference cannot hold C4 itself (int-indexed containers, hours of CPU time); every stage
+    is O(voxels) at fixed radii, so the per-voxel rate carries over (a small crop has fewer
+    in-image window visits per voxel, which favours the reference).  One extra, untimed-by-the-
+    driver 256^3 pass with per-stage seconds is added at N = 1 when the host is fast enough."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     shape = WORKLOADS.get(args.workload, WORKLOADS["C4"])
+    t_start = time.perf_counter()
     for _ in range(args.warmup):
         cpu_reference_run(CPU_SAMPLE)
     ts = []
-    cores, kind = os.cpu_count(), "reference"
-    for _ in range(args.steps):
-        dt, cores, kind = cpu_reference_run(CPU_SAMPLE)
+    cores, kind, stages = host_threads(), "reference", None
+    for k in range(args.steps):
+        dt, cores, kind, st = cpu_reference_run(CPU_SAMPLE, staged=(k == args.steps - 1))
+        stages = st or stages
         ts.append(dt)
     dt = float(np.mean(ts))
     val = np.prod(CPU_SAMPLE) / dt / 1e9
-    sample = ("%dx%dx%d crop of the synthetic workload, same parameters (sigma 3, vote radius 20, "
-              "tv-best 0.05), one full pipeline pass per step" % CPU_SAMPLE)
+    big = None
+    spent = time.perf_counter() - t_start
+    # a 256^3 pass costs ~8.7 crops (more in-image windows per voxel); only when it fits in ~4 minutes more
+    if world == 1 and not args.no_cpu_big and 9.0 * dt < 240.0 and spent + 9.0 * dt < 600.0:
+        bshape = (256, 256, 256)
+        bdt, _, _, bst = cpu_reference_run(bshape, staged=True)
+        big = {"shape_zyx": list(bshape), "seconds": bdt, "value": float(np.prod(bshape)) / bdt / 1e9,
+               "unit": "Gvoxel/s", "stage_seconds": bst}
+    cfg = workload_config(args.workload, shape)
+    cfg["cpu_sample"] = {"shape_zyx": list(CPU_SAMPLE), "note": "the reference arm times this crop, not the full "
+                         "volume; value is a per-voxel rate"}
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gvoxel/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, shape),
-            "cpu_baseline": {"value": val, "unit": "Gvoxel/s", "cores": cores, "kind": kind, "sample": sample},
+            "config": cfg,
+            "cpu_baseline": {"value": val, "unit": "Gvoxel/s", "cores": cores, "kind": kind,
+                             "sample": cpu_sample_text(CPU_SAMPLE), "stage_seconds_last_step": stages,
+                             "point_256": big},
             "e2e": {"value": val, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=RESULT_OUT, flush=True)
@@ -282,12 +354,13 @@ def main():
         shape = tuple(int(v) for v in args.shape.split(","))
         name = "custom"
     nz, ny, nx = shape
-    # C4 needs ~100 GB of HBM on one GPU; fall back (and say so) on a smaller device
+    # C4 needs ~100 GB of HBM on one GPU: a device that cannot hold the workload is an error, not
+    # a reason to measure something else
     free_b, total_b = torch.cuda.mem_get_info()
     need = 6.5 * 4 * nz * ny * nx / world
-    if need > free_b and name == "C4":
-        name, shape = "C2", WORKLOADS["C2"]
-        nz, ny, nx = shape
+    if need > free_b:
+        raise SystemExit("bench.py: workload %s needs ~%.0f GB of HBM per GPU at N=%d, %.0f GB free" %
+                         (name, need / 1e9, world, free_b / 1e9))
 
     ctx = visfd_b200.Context(local, stream=torch.cuda.current_stream().cuda_stream)
     params = MembraneParams(SIGMA, RATIO, visfd_b200.DECREASING_EIVALS, TV_BEST, 1, TV_SIGMA, 4, SQ2)
@@ -338,6 +411,22 @@ def main():
     if world > 1:
         dist.all_reduce(lt)
     launches = int(lt.item())
+
+    # ---- checksum of the result volume: identical at every N if the slabs reproduce one GPU ------
+    # exact integer arithmetic on the float bit patterns (associative, so the split does not matter):
+    # sum of the bits, and the same weighted by the global plane number (catches misplaced planes)
+    plane_bits = torch.stack([out[z].view(torch.int32).sum(dtype=torch.int64) for z in range(out.shape[0])])
+    zw = torch.arange(z0 + 1, z1 + 1, device=dev, dtype=torch.int64)
+    ck = torch.stack([plane_bits.sum(), (plane_bits * zw).sum()])
+    f64 = out.sum(dtype=torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(ck)
+        dist.all_reduce(f64)
+    checksum = {"bits_sum_i64": int(ck[0].item()), "plane_weighted_bits_sum_i64": int(ck[1].item()),
+                "f64_sum": float(f64.item()),
+                "note": "wrapping int64 sums of the float32 bit patterns of the output volume (exact, order "
+                        "independent): equal at every N iff the volumes are bit-identical up to permutation "
+                        "within a plane"}
 
     # ---- roofline of the dominant kernel (rank 0's launch) ----------------------------------
     if world == 1:
@@ -423,18 +512,16 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        dt, cores, kind = cpu_reference_run(CPU_SAMPLE)
+        dt, cores, kind, st = cpu_reference_run(CPU_SAMPLE, staged=True)
         cpu = {"value": float(np.prod(CPU_SAMPLE)) / dt / 1e9, "unit": "Gvoxel/s", "cores": cores, "kind": kind,
-               "seconds": dt,
-               "sample": "%dx%dx%d crop of the synthetic workload with the same parameters (sigma 3, vote radius "
-                         "20, tv-best 0.05): one pipeline pass of the unmodified reference (OpenMP, all host "
-                         "threads)" % CPU_SAMPLE}
+               "seconds": dt, "stage_seconds": st, "sample": cpu_sample_text(CPU_SAMPLE)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": n_vox / (ms_step * 1e-3) / 1e9, "unit": "Gvoxel/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(name, shape), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "checksum": checksum,
                 "roofline": roofline, "roofline_gauss": gauss, "roofline_ridge": ridge, "gauss_c2": gauss_c2, "blob_c3": blob_c3,
                 "cpu_baseline": cpu,
                 "stage_ms_rank0_last_step": stage, "halo_planes": pipe.plan.halo if world > 1 else 0}

@@ -51,6 +51,7 @@ def load_library():
     lib.visfd_cuda_last_error.restype = C.c_char_p
     lib.visfd_cuda_launch_count.restype = _i64
     lib.visfd_cuda_last_voter_count.restype = _i64
+    lib.visfd_cuda_last_tv_kernel.restype = C.c_int
     lib.visfd_cuda_stage_ms.restype = _d
     lib.visfd_cuda_key_to_float.restype = _f
     lib.visfd_cuda_set_timing.restype = None
@@ -235,6 +236,10 @@ class Context:
 
     def last_voter_count(self):
         return self.lib.visfd_cuda_last_voter_count(self.h)
+
+    def last_tv_kernel(self):
+        """Voting kernel of the last call: 0 = MUFU decay, 1 = r^2 table, 2 = r^2 table with clamped index."""
+        return self.lib.visfd_cuda_last_tv_kernel(self.h)
 
     def fp32_peak(self, ms=200.0, packed=False, three_operand=False):
         t = _d()

@@ -593,6 +593,7 @@ int visfd_cuda_blob_finalize(float minima_threshold, float maxima_threshold, int
 
 // ---- bookkeeping -------------------------------------------------------------------------------------------
 int64_t visfd_cuda_last_voter_count(visfd_ctx *ctx) { return ctx ? ctx->last_voters : -1; }
+int visfd_cuda_last_tv_kernel(visfd_ctx *ctx) { return ctx ? ctx->last_tv_kernel : -1; }
 
 int visfd_cuda_tv_count_pairs(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *saliency,
                               float threshold, const float *mask_src, const float *mask_dst, int halfwidth,

@@ -47,6 +47,7 @@ struct visfd_ctx {
   cudaStream_t copy_stream = nullptr;       // lazily created: D2H of finished result chunks behind the kernels
   int64_t launches = 0;
   int64_t last_voters = 0;
+  int last_tv_kernel = 0;                   // voting kernel of the last call: 0 MUFU, 1 table, 2 table with clamped index
   bool fast_gauss = false;                  // FFMA sweeps instead of the bit-exact mul+add
   bool use_tma = true;                      // stage the sweeps' tiles with TMA (VISFD_CUDA_NO_TMA=1: cp.async)
   bool timing = true;                       // record per-stage CUDA events

@@ -3,22 +3,26 @@
 //
 // The reference visits all (2hw+1)^3 offsets of every receiver and skips the ~95 % of
 // them whose voter has zero saliency.  Here the voters (saliency != 0 after the cut,
-// mask != 0) are first compacted into a list ordered by 8x8x8 BRICK (count -> exclusive
-// scan -> fill: three streaming passes over the saliency volume), 32 B per voter:
-//     A = {x, y, z, saliency * mask_weight / table_total}   B = {nx, ny, nz, 0}
-// The gather kernel runs one CTA per 8x8x8 receiver tile.  The tile's neighbourhood is
-// a set of <= (2R+2)(2R+1) brick ROWS (R = ceil(hw/8)), each a contiguous range of the
-// voter list trimmed to the bricks that can reach the tile; the ranges are streamed
-// through a double-buffered shared-memory ring with cp.async (LDGSTS).  Each of the 8
-// warps owns a 4x4x4 receiver patch (32 lanes x 2 z-adjacent receivers per lane, 12
-// register accumulators); lanes first test 32 voters in parallel against the patch
-// (ballot), then the warp walks the surviving voters, broadcasting each one from shared
-// memory.  Per (receiver, voter) pair that is ~33 FP32-pipe instructions (35 FLOP by
-// the SURVEY's count), with no table lookup: the radial decay exp(-r^2/sigma^2) is one
-// MUFU.EX2 and 1/r one MUFU.RSQ.  The reference's decay TABLE is only needed for two
-// things, both computed on the host with the reference's own float expressions
-// (lib/visfd/filter3d.hpp:546-601): the normalisation constant (sum over the cube) and
-// which lattice points on the shell r^2 == hw^2 survive the truncation threshold.
+// mask != 0) are first compacted into a list ordered by 4x4x4 BRICK (count -> exclusive
+// scan -> fill -> direction: streaming passes over the saliency volume, made by kernels that
+// work on 8x8x8 regions), 48 B per voter, laid out as the voting kernels consume them
+// (struct VoterRec).  The gather runs one WARP per 4x4x4 receiver patch (lane = (x, y, half);
+// four z-receivers per lane; the two half-warps take different voters): it builds the table of
+// brick rows that can reach the patch, streams their voters through an exact voter-to-patch
+// distance test into a warp-private cp.async ring in shared memory, and drains the ring 32
+// voters at a time.  Two kernels share that code:
+//   * tv_gather_kernel     -- 4 warps per CTA (one 8x8x4 tile), radial decay by MUFU.EX2 / MUFU.RCP;
+//                             every exponent, curves, non-positive weights, mixed support shells.
+//   * tv_gather_lut_kernel -- persistent, one 16-warp CTA per SM; exp(-r^2/2 sigma^2) (zero outside
+//                             the support) and -1/r^2 come from a shared-memory table indexed by
+//                             the INTEGER r^2 (positions are lattice points), 16 replicas so that
+//                             the lanes of a half-warp never share a bank.  Exponent 4, positive
+//                             weights, vote radius <= 24: the filter_mrc default and BASELINE's
+//                             configurations.  No MUFU, no support mask in the loop.
+// The reference's decay TABLE (lib/visfd/filter3d.hpp:546-601) is only needed for two things,
+// both computed on the host with the reference's own float expressions: the normalisation
+// constant (sum over the cube) and which lattice points on the shell r^2 == hw^2 survive the
+// truncation threshold.
 //
 // Epilogue (fused, accumulators still in registers): optional store of the 6-component
 // tensor (-save-progress) and DiagonalizeFlatSym3 + ScoreTensorPlanar/Linear
@@ -264,6 +268,9 @@ struct __align__(16) VoterRec {
   float4 a;  // {-x, -y, -z, log2(4w)/2}
   float4 b;  // {nx, ny, nz, log2(4w)}
   float4 c;  // {nx/2, ny/2, nz/2, 4w}       w = saliency * mask weight / table total
+  // table kernel (lut): a = {-x, -y, -z, L^2}, b = {L nx, L ny, L nz, L}, c = {L nx/2, L ny/2, L nz/2, 0}
+  // with L = (4w)^(1/6): the vote u = sqrt(4w decay) cos^2 (n/2 - q r) picks up L from the dot
+  // product, L^2 from cos^2 and L from n/2, so the weight costs no instruction in the loop
 };
 
 struct DirSrc {
@@ -315,7 +322,7 @@ __device__ __forceinline__ void voter_direction(const DirSrc &d, int nx, int ny,
 // Pass 1 of the fill (one CTA per run of VB bricks): positions and weights in brick order, voxels of a
 // brick in thread order (z, y, x).
 __global__ void __launch_bounds__(BR3, 2)
-voter_fill_kernel(VoterSrc v, i64 n_regions, const uint32_t *__restrict__ off, float inv_total,
+voter_fill_kernel(VoterSrc v, i64 n_regions, const uint32_t *__restrict__ off, float inv_total, bool lut,
                   VoterRec *__restrict__ rec, uint32_t *__restrict__ nonpos_flag) {
   __shared__ uint32_t wsum[VB][2][BR3 / 32];   // per region, x half, warp
   const i64 b0 = (i64)blockIdx.x * VB;
@@ -356,9 +363,17 @@ voter_fill_kernel(VoterSrc v, i64 n_regions, const uint32_t *__restrict__ off, f
       // the three forms of the weight the gather kernels fold into their arithmetic (vote())
       const float w4 = 4.0f * wgt, l4 = log2f(w4);
       VoterRec *r = rec + off[voter_brick(v, bp, sb)] + rank;
-      r->a = make_float4(-(float)(bp.bx * BR + tx), -(float)(bp.by * BR + ty), -(float)(bp.bz * BR + tz), 0.5f * l4);
-      r->b.w = l4;
-      r->c.w = w4;
+      const float px = -(float)(bp.bx * BR + tx), py = -(float)(bp.by * BR + ty), pz = -(float)(bp.bz * BR + tz);
+      if (lut) {   // only used when every weight is positive (checked by the host before the launch)
+        const float lam = (float)pow((double)fmaxf(w4, 0.0f), 1.0 / 6.0);
+        r->a = make_float4(px, py, pz, lam * lam);
+        r->b.w = lam;
+        r->c.w = 0.0f;
+      } else {
+        r->a = make_float4(px, py, pz, 0.5f * l4);
+        r->b.w = l4;
+        r->c.w = w4;
+      }
     }
     next_brick(v, bp);
   }
@@ -367,13 +382,17 @@ voter_fill_kernel(VoterSrc v, i64 n_regions, const uint32_t *__restrict__ off, f
 // Pass 2: one THREAD per voter (dense lanes -- in the brick pass only ~5 % of the lanes are
 // voters and the double-precision eigenvector would run at that lane efficiency).
 __global__ void __launch_bounds__(256)
-voter_direction_kernel(DirSrc d, int nx, int ny, uint32_t n_voters, VoterRec *__restrict__ rec) {
+voter_direction_kernel(DirSrc d, int nx, int ny, uint32_t n_voters, bool lut, VoterRec *__restrict__ rec) {
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= n_voters) return;
   VoterRec *r = rec + i;
   const float4 a = r->a;
   float n[3];
   voter_direction(d, nx, ny, (int)(-a.x), (int)(-a.y), (i64)(-a.z), n);
+  if (lut) {
+    const float lam = r->b.w;
+    n[0] *= lam; n[1] *= lam; n[2] *= lam;
+  }
   r->b.x = n[0]; r->b.y = n[1]; r->b.z = n[2];
   r->c.x = 0.5f * n[0]; r->c.y = 0.5f * n[1]; r->c.z = 0.5f * n[2];
 }
@@ -402,6 +421,11 @@ struct GatherArgs {
   float *tensor;          // own-planes-indexed * 6, or NULL
   float *score;           // own-planes-indexed, or NULL
   int order, score_kind;
+  // table kernel only
+  const float2 *lut;      // n_lut entries {sqrt(decay(r2)) or 0 outside the support, -1/r2 (0 at r2 = 0)}
+  int n_lut;              // the last entry is {0, 0}: r2 is clamped to it when the table is shorter than the reach
+  unsigned n_tiles;       // 8x8x4 receiver tiles of this launch
+  unsigned *ticket;       // device counter handing out tiles, zeroed before the launch
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -543,18 +567,71 @@ __device__ __forceinline__ void vote(const VoterRec *q, float fx, float fy, floa
   vote_pair<EXPO, CURVES, POSW, SHELL>(rx, ry, rxy2, dxy, fz23, ea, eb, ec, g, negc, lim_in, T + 6);
 }
 
+
+// ---- table variant (exponent 4, weights > 0) ---------------------------------------------------
+// r2 is an integer < 2^16, so LUT_MAGIC + r2 is exact and its bit pattern is bits(LUT_MAGIC) + 128 r2:
+// a byte offset into a table of 128-byte rows (16 replicas of {E, -1/r2}; a lane reads replica lane & 15,
+// so the 16 lanes of a half-warp -- which share the voter -- cover all 32 banks exactly once).
+constexpr float LUT_MAGIC = 65536.0f;   // ulp 2^-7
+constexpr int LUT_ROW = 128;            // bytes per r2
+constexpr int LUT_MAX_HW = 24;
+struct LutState {
+  unsigned tab;      // shared-window address of the lane's replica, minus bits(LUT_MAGIC)
+  float r2m_max;     // LUT_MAGIC + (n_lut - 1)
+};
+__device__ __forceinline__ float2 lut_fetch(float r2m, unsigned tab) {
+  return *reinterpret_cast<const float2 *>(__cvta_shared_to_generic(__float_as_uint(r2m) + tab));
+}
+template <bool CURVES, bool CLAMP>
+__device__ __forceinline__ void vote_pair_lut(float rx, float ry, float rxy2m, float dxy, float2 fz, const float4 &ea,
+                                              const float4 &eb, const float4 &ec, const LutState &L, float2 T[6]) {
+  const float2 rz = __fadd2_rn(fz, bc(ea.z));
+  float2 r2m = __ffma2_rn(rz, rz, bc(rxy2m));
+  if (CLAMP) { r2m.x = fminf(r2m.x, L.r2m_max); r2m.y = fminf(r2m.y, L.r2m_max); }
+  const float2 d = __ffma2_rn(rz, bc(eb.z), bc(dxy));        // L (r.n)
+  const float2 t0 = lut_fetch(r2m.x, L.tab), t1 = lut_fetch(r2m.y, L.tab);
+  const float2 ee = make_float2(t0.x, t1.x), ninv = make_float2(t0.y, t1.y);
+  const float2 qn = __fmul2_rn(d, ninv);                     // -L q
+  float2 ang2;                                               // L^2 cos^2 (surfaces) / -L^2 sin^2 (curves)
+  if (CURVES) ang2 = __fmul2_rn(qn, d);
+  else ang2 = __ffma2_rn(qn, d, bc(ea.w));
+  const float2 w = __fmul2_rn(ee, ang2);                     // sign irrelevant: squared below
+  const float2 hx = __ffma2_rn(qn, bc(rx), bc(ec.x));        // L (n/2 - q r)
+  const float2 hy = __ffma2_rn(qn, bc(ry), bc(ec.y));
+  const float2 hz = __ffma2_rn(qn, rz, bc(ec.z));
+  const float2 wx = __fmul2_rn(w, hx), wy = __fmul2_rn(w, hy), wz = __fmul2_rn(w, hz);
+  T[0] = __ffma2_rn(wx, wx, T[0]);
+  T[3] = __ffma2_rn(wx, wy, T[3]);
+  T[5] = __ffma2_rn(wx, wz, T[5]);
+  T[1] = __ffma2_rn(wy, wy, T[1]);
+  T[4] = __ffma2_rn(wy, wz, T[4]);
+  T[2] = __ffma2_rn(wz, wz, T[2]);
+}
+template <bool CURVES, bool CLAMP>
+__device__ __forceinline__ void vote_lut(const VoterRec *q, float fx, float fy, float2 fz01, float2 fz23, const LutState &L,
+                                         float2 T[12]) {
+  const float4 ea = q->a, eb = q->b, ec = q->c;
+  const float rx = fx + ea.x, ry = fy + ea.y;
+  const float rxy2m = fmaf(ry, ry, fmaf(rx, rx, LUT_MAGIC));
+  const float dxy = fmaf(ry, eb.y, rx * eb.x);
+  vote_pair_lut<CURVES, CLAMP>(rx, ry, rxy2m, dxy, fz01, ea, eb, ec, L, T);
+  vote_pair_lut<CURVES, CLAMP>(rx, ry, rxy2m, dxy, fz23, ea, eb, ec, L, T + 6);
+}
+
 // n consecutive ring entries (n a multiple of 4; a drain never wraps, see the kernel): the
 // lanes of half-warp h take entries h, h+2, h+4, ... -- two voters per warp iteration.
-template <int EXPO, bool CURVES, bool POSW, bool SHELL>
+// LUT: 0 = decay by MUFU (vote), 1 = table covering the whole reach, 2 = table with clamped index
+template <int EXPO, bool CURVES, bool POSW, bool SHELL, int LUT>
 __device__ __forceinline__ void drain(const VoterRec *q, int n, float fx, float fy, float2 fz01, float2 fz23,
-                                      const GatherArgs &g, float negc, float lim_in, float2 T[12]) {
+                                      const GatherArgs &g, float negc, float lim_in, const LutState &L, float2 T[12]) {
   const VoterRec *end = q + n;
 #pragma unroll 1
   for (; q < end; q += 8) {
-    vote<EXPO, CURVES, POSW, SHELL>(q, fx, fy, fz01, fz23, g, negc, lim_in, T);
-    vote<EXPO, CURVES, POSW, SHELL>(q + 2, fx, fy, fz01, fz23, g, negc, lim_in, T);
-    vote<EXPO, CURVES, POSW, SHELL>(q + 4, fx, fy, fz01, fz23, g, negc, lim_in, T);
-    vote<EXPO, CURVES, POSW, SHELL>(q + 6, fx, fy, fz01, fz23, g, negc, lim_in, T);
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) {
+      if (LUT) vote_lut<CURVES, LUT == 2>(q + u, fx, fy, fz01, fz23, L, T);
+      else vote<EXPO, CURVES, POSW, SHELL>(q + u, fx, fy, fz01, fz23, g, negc, lim_in, T);
+    }
   }
 }
 // One WARP per 4x4x4 receiver patch.  Lane = (x, y, h): the lanes of half-warp h hold all four
@@ -578,14 +655,10 @@ __device__ __forceinline__ void drain(const VoterRec *q, int n, float fx, float 
 // Before it the ring holds <= 95 voters, it adds <= 64 (159 < 160 live), and it drains the
 // whole groups of 32 among the voters queued before it -- all of which belong to cp.async
 // groups older than the newest one -- leaving <= 31 + 64.
-template <int EXPO, bool CURVES, bool POSW, bool SHELL>
-__global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(GatherArgs g) {
-  extern __shared__ __align__(16) unsigned char tv_smem[];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const unsigned slot = blockIdx.x * TV_WARPS + (tid >> 5);   // warp slot: 4 per tile
+template <int EXPO, bool CURVES, bool POSW, bool SHELL, int LUT>
+__device__ __forceinline__ void gather_patch(const GatherArgs &g, const unsigned slot, unsigned char *mine, const LutState &L) {
+  const int lane = threadIdx.x & 31;
   const int warp = slot & 3;
-  const size_t per_warp = TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t);
-  unsigned char *mine = tv_smem + (tid >> 5) * ((per_warp + 15) & ~(size_t)15);
   VoterRec *ring = reinterpret_cast<VoterRec *>(mine);
   uint32_t *row_start = reinterpret_cast<uint32_t *>(ring + TV_QCAP);
   uint32_t *row_pref = row_start + g.row_cap;  // [row_cap + 1]
@@ -702,7 +775,7 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
       cp_async_wait<1>();
       __syncwarp();
       for (int d = 0; d < ndrain; d += TV_DRAIN) {
-        drain<EXPO, CURVES, POSW, SHELL>(ring + head + half, TV_DRAIN, fx, fy, fz01, fz23, g, negc, lim_in, T);
+        drain<EXPO, CURVES, POSW, SHELL, LUT>(ring + head + half, TV_DRAIN, fx, fy, fz01, fz23, g, negc, lim_in, L, T);
         head = (head + TV_DRAIN == TV_QCAP) ? 0 : head + TV_DRAIN;
       }
       cnt -= ndrain;
@@ -714,16 +787,22 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
   if (lane < ((8 - (cnt & 7)) & 7)) {
     int slot = head + cnt + lane;
     if (slot >= TV_QCAP) slot -= TV_QCAP;
-    const float ninf = __int_as_float(0xff800000u);  // ex2(-inf) = 0
-    ring[slot].a = make_float4(1.0e4f, 1.0e4f, 1.0e4f, ninf);
-    ring[slot].b = make_float4(0.f, 0.f, 0.f, ninf);
+    if (LUT) {
+      // a zero vote: the lane's own position (r = 0, so the index stays inside the table) and L = 0
+      ring[slot].a = make_float4(-(float)px, -(float)py, -(float)pz, 0.0f);
+      ring[slot].b = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const float ninf = __int_as_float(0xff800000u);  // ex2(-inf) = 0
+      ring[slot].a = make_float4(1.0e4f, 1.0e4f, 1.0e4f, ninf);
+      ring[slot].b = make_float4(0.f, 0.f, 0.f, ninf);
+    }
     ring[slot].c = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncwarp();
   cnt = (cnt + 7) & ~7;
   while (cnt > 0) {
     const int n = min(cnt, min(TV_DRAIN, TV_QCAP - head));
-    drain<EXPO, CURVES, POSW, SHELL>(ring + head + half, n, fx, fy, fz01, fz23, g, negc, lim_in, T);
+    drain<EXPO, CURVES, POSW, SHELL, LUT>(ring + head + half, n, fx, fy, fz01, fz23, g, negc, lim_in, L, T);
     head = (head + n == TV_QCAP) ? 0 : head + n;
     cnt -= n;
   }
@@ -770,6 +849,68 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
   }
 }
 
+
+// 4 warps per CTA = one 8x8x4 receiver tile; decay by MUFU.
+template <int EXPO, bool CURVES, bool POSW, bool SHELL>
+__global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(GatherArgs g) {
+  extern __shared__ __align__(16) unsigned char tv_smem[];
+  const unsigned slot = blockIdx.x * TV_WARPS + (threadIdx.x >> 5);   // warp slot: 4 per tile
+  const size_t per_warp = TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t);
+  unsigned char *mine = tv_smem + (threadIdx.x >> 5) * ((per_warp + 15) & ~(size_t)15);
+  LutState L{0u, 0.0f};
+  gather_patch<EXPO, CURVES, POSW, SHELL, 0>(g, slot, mine, L);
+}
+
+// Persistent table kernel: one CTA of 16 warps per SM, the table once per CTA.  The warps never wait for
+// each other after the table is in place.  Work is handed out per QUAD of warps (4 quads per CTA): the four
+// patches of an 8x8x4 tile go to the four next tickets of one quad, so that they run on the same SM at about the
+// same time and find each other's candidates in L1, and a warp that finishes early takes the first patch of the
+// quad's next tile instead of idling.  The warp that draws a tile's first ticket fetches the tile number from the
+// device-wide counter and publishes it in shared memory; the other three pick it up there.
+constexpr int LUT_WARPS = 16, LUT_QUADS = LUT_WARPS / 4, LUT_SEQ = 8;   // a slot is reused 32 tickets later
+template <bool CURVES, bool CLAMP>
+__global__ void __launch_bounds__(32 * LUT_WARPS, 1) tv_gather_lut_kernel(GatherArgs g) {
+  extern __shared__ __align__(16) unsigned char tv_smem[];
+  __shared__ unsigned quad_ticket[LUT_QUADS];
+  __shared__ volatile unsigned quad_tile[LUT_QUADS][LUT_SEQ], quad_seq[LUT_QUADS][LUT_SEQ];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, quad = w >> 2;
+  const size_t tab_bytes = (size_t)g.n_lut * LUT_ROW;
+  {
+    float2 *tab = reinterpret_cast<float2 *>(tv_smem);
+    for (int i = threadIdx.x; i < g.n_lut * (LUT_ROW / 8); i += 32 * LUT_WARPS) tab[i] = __ldg(g.lut + i / (LUT_ROW / 8));
+    if (threadIdx.x < LUT_QUADS) quad_ticket[threadIdx.x] = 0u;
+    if (threadIdx.x < LUT_QUADS * LUT_SEQ) quad_seq[threadIdx.x / LUT_SEQ][threadIdx.x % LUT_SEQ] = 0u;
+  }
+  __syncthreads();
+  const size_t per_warp = (TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t) + 15) & ~(size_t)15;
+  unsigned char *mine = tv_smem + tab_bytes + w * per_warp;
+  LutState L;
+  L.tab = (unsigned)__cvta_generic_to_shared(tv_smem) + 8u * (lane & 15) - __float_as_uint(LUT_MAGIC);
+  L.r2m_max = LUT_MAGIC + (float)(g.n_lut - 1);
+  for (;;) {
+    unsigned t = 0, tile = 0;
+    if (lane == 0) {
+      t = atomicAdd(&quad_ticket[quad], 1u);
+      const unsigned k = t >> 2, s = k % LUT_SEQ;
+      if ((t & 3u) == 0u) {
+        tile = atomicAdd(g.ticket, 1u);
+        quad_tile[quad][s] = tile;
+        __threadfence_block();
+        quad_seq[quad][s] = k + 1u;
+      } else {
+        while (quad_seq[quad][s] != k + 1u) {}
+        __threadfence_block();
+        tile = quad_tile[quad][s];
+      }
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= g.n_tiles) break;   // the counter only grows: every later ticket of this quad ends here too
+    gather_patch<4, CURVES, true, false, CLAMP ? 2 : 1>(g, tile * 4u + (t & 3u), mine, L);
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------
@@ -799,6 +940,12 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   Scratch<uint32_t> counts(ctx, n_bricks), off(ctx, n_bricks + 1);
   const i64 n_scan_blocks = (n_bricks + SCAN_B - 1) / SCAN_B;
   Scratch<uint32_t> sums(ctx, n_scan_blocks + 2);   // block sums, [n] = total, [n+1] = non-positive-weight flag
+  // which kernel: the table kernel wants exponent 4, positive weights (known after the fill), a support
+  // whose shell is all kept or all dropped, and a radius whose table fits beside the voter rings
+  const bool mixed_shell = info.shell_total != 0 && info.shell_kept != 0 && info.shell_kept != info.shell_total;
+  const bool shell_in = info.shell_total != 0 && info.shell_kept == info.shell_total;
+  const char *no_lut_env = getenv("VISFD_CUDA_NO_LUT");   // tests: force the MUFU kernel
+  bool use_lut = p.exponent == 4 && !mixed_shell && hw <= LUT_MAX_HW && !(no_lut_env && atoi(no_lut_env));
   uint32_t n_voters = 0, nonpos = 0;
   Scratch<VoterRec> rec;
   {
@@ -820,15 +967,21 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
     if (n_voters > 0) {
       DirSrc ds{direction, smoothed, ridge_sigma, eival_order, z_offset, nz_global};
       VCK(cudaMemsetAsync(sums.get() + n_scan_blocks + 1, 0, sizeof(uint32_t), ctx->stream));
-      voter_fill_kernel<<<(unsigned)div_up(n_regions, VB), BR3, 0, ctx->stream>>>(vs, n_regions, off.get(), 1.0f / info.total,
-                                                                                 rec.get(), sums.get() + n_scan_blocks + 1);
+      for (;;) {
+        voter_fill_kernel<<<(unsigned)div_up(n_regions, VB), BR3, 0, ctx->stream>>>(
+            vs, n_regions, off.get(), 1.0f / info.total, use_lut, rec.get(), sums.get() + n_scan_blocks + 1);
+        VCK(cudaGetLastError());
+        ctx->count_launch();
+        VCK(cudaMemcpyAsync(&nonpos, sums.get() + n_scan_blocks + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+        VCK(cudaStreamSynchronize(ctx->stream));
+        if (!(use_lut && nonpos)) break;
+        use_lut = false;   // a weight <= 0 (negative saliency or mask weight): records for the MUFU kernel instead
+      }
+      voter_direction_kernel<<<div_up(n_voters, 256), 256, 0, ctx->stream>>>(ds, (int)nx, (int)ny, n_voters, use_lut,
+                                                                            rec.get());
       VCK(cudaGetLastError());
-      voter_direction_kernel<<<div_up(n_voters, 256), 256, 0, ctx->stream>>>(ds, (int)nx, (int)ny, n_voters, rec.get());
-      VCK(cudaGetLastError());
-      ctx->count_launch(2);
-      VCK(cudaMemcpyAsync(&nonpos, sums.get() + n_scan_blocks + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                          ctx->stream));
-      VCK(cudaStreamSynchronize(ctx->stream));
+      ctx->count_launch();
     }
   }
   ctx->last_voters = n_voters;
@@ -848,14 +1001,13 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   g.hw = hw; g.hw2 = (float)(hw * hw);
   { const int per_axis = ((2 * hw + 3) >> VSH) + 2; g.row_cap = per_axis * per_axis; }
   // lattice points on the shell r2 == hw^2: all kept / all dropped / mixed (see vote())
-  const bool mixed_shell = info.shell_total != 0 && info.shell_kept != 0 && info.shell_kept != info.shell_total;
-  const bool shell_in = info.shell_total != 0 && info.shell_kept == info.shell_total;
   g.lim_in = g.hw2 + ((shell_in && !mixed_shell) ? 0.5f : -0.5f);
   g.lim_pass = g.hw2 + ((shell_in || mixed_shell) ? 0.5f : -0.5f);
   g.neg_c = (float)(-1.4426950408889634 / ((double)p.sigma * (double)p.sigma));
   g.half_exp = 0.5f * (float)p.exponent;
   g.mask_dst = mask_dst; g.tensor = tensor; g.score = score;
   g.order = eival_order; g.score_kind = score_kind;
+  g.lut = nullptr; g.n_lut = 0; g.n_tiles = 0; g.ticket = nullptr;
   // receiver planes in chunks (multiples of the 8-plane tile): one launch each, so that a
   // finished chunk of the result can travel to the host while the next one is computed
   const i64 planes = own_z1 - own_z0;
@@ -872,12 +1024,63 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   VREQUIRE((i64)g.ntx * g.nty * div_up(chunk_planes, TV_TILE_Z) * 4 / TV_WARPS < 2147483647LL,
            "too many receiver tiles for one launch");
   std::vector<cudaEvent_t> chunk_done;
+  // ---- table kernel set-up ---------------------------------------------------------------------
+  const size_t per_warp = (TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t) + 15) & ~(size_t)15;
+  Scratch<float2> lut;
+  Scratch<unsigned> tickets;
+  int lut_mode = 0;   // 0: MUFU kernel, 1: table over the whole reach, 2: table up to the support, clamped index
+  size_t lut_smem = 0;
+  if (use_lut && n_voters > 0) {
+    int smem_max = 0;
+    VCK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    const size_t budget = (size_t)smem_max - 1024;   // the kernel's static shared memory (work tickets)
+    // largest r2 between a receiver of a 4x4x4 patch and a voter the cull lets through (gap vector g, |g|^2 < lim_pass)
+    int r2_reach = 27;
+    for (int gz = 0; gz <= hw; gz++)
+      for (int gy = 0; gy <= hw; gy++)
+        for (int gx = 0; gx <= hw; gx++)
+          if ((float)(gx * gx + gy * gy + gz * gz) < g.lim_pass)
+            r2_reach = std::max(r2_reach, (gx + 3) * (gx + 3) + (gy + 3) * (gy + 3) + (gz + 3) * (gz + 3));
+    const int r2_in = (int)floorf(g.lim_in);          // largest r2 with a non-zero weight (lim_in = hw^2 +- 0.5)
+    const int n_full = r2_reach + 1, n_clamped = r2_in + 2;
+    const char *mode_env = getenv("VISFD_CUDA_LUT_MODE");   // tests / tuning: 1 or 2
+    const int want = mode_env ? atoi(mode_env) : 0;
+    if (want != 2 && (size_t)n_full * LUT_ROW + LUT_WARPS * per_warp <= budget) { lut_mode = 1; g.n_lut = n_full; }
+    else if ((size_t)n_clamped * LUT_ROW + LUT_WARPS * per_warp <= budget) { lut_mode = 2; g.n_lut = n_clamped; }
+    if (lut_mode) {
+      std::vector<float2> h(g.n_lut);
+      for (int r2 = 0; r2 < g.n_lut; r2++) {
+        const float e = ((float)r2 < g.lim_in) ? (float)exp(-0.5 * (double)r2 / ((double)p.sigma * (double)p.sigma)) : 0.0f;
+        h[r2] = make_float2(e, r2 ? (float)(-1.0 / (double)r2) : 0.0f);
+      }
+      if (lut_mode == 2) h[g.n_lut - 1] = make_float2(0.0f, 0.0f);
+      lut.reset(ctx, h.size());
+      VCK(cudaMemcpyAsync(lut.get(), h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+      VCK(cudaStreamSynchronize(ctx->stream));   // h goes out of scope
+      g.lut = lut.get();
+      lut_smem = (size_t)g.n_lut * LUT_ROW + LUT_WARPS * per_warp;
+    }
+  }
+  if (use_lut && n_voters > 0 && !lut_mode) {
+    // records were written for the table kernel but no table fits: rewrite them for the MUFU kernel
+    voter_fill_kernel<<<(unsigned)div_up(n_regions, VB), BR3, 0, ctx->stream>>>(
+        vs, n_regions, off.get(), 1.0f / info.total, false, rec.get(), sums.get() + n_scan_blocks + 1);
+    VCK(cudaGetLastError());
+    DirSrc ds{direction, smoothed, ridge_sigma, eival_order, z_offset, nz_global};
+    voter_direction_kernel<<<div_up(n_voters, 256), 256, 0, ctx->stream>>>(ds, (int)nx, (int)ny, n_voters, false, rec.get());
+    VCK(cudaGetLastError());
+    ctx->count_launch(2);
+  }
+  ctx->last_tv_kernel = lut_mode;
   const GatherArgs g_all = g;
+  if (lut_mode) {
+    tickets.reset(ctx, (size_t)n_chunks);
+    VCK(cudaMemsetAsync(tickets.get(), 0, (size_t)n_chunks * sizeof(unsigned), ctx->stream));
+  }
   {
     StageTimer t(ctx, "tv");
     // POSW: all voter weights > 0 (always true for the planar ridge score), so log2(weight)
     // rides in the decay exponent
-    const size_t per_warp = (TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t) + 15) & ~(size_t)15;
     const size_t smem = (TV_THREADS / 32) * per_warp;
     for (int c = 0; c < n_chunks; c++) {
     g = g_all;
@@ -887,6 +1090,20 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
     if (g_all.score) g.score = g_all.score + chunk_off;
     if (g_all.tensor) g.tensor = g_all.tensor + 6 * chunk_off;
     const unsigned grid = (unsigned)((i64)g.ntx * g.nty * div_up(g.own_z1 - g.own_z0, TV_TILE_Z) * 4 / TV_WARPS);
+    if (lut_mode) {
+      g.n_tiles = grid;   // one 4-warp tile per CTA of the MUFU kernel
+      g.ticket = tickets.get() + c;
+      const unsigned ctas = (unsigned)std::min<i64>(ctx->sm_count, ((i64)grid + LUT_QUADS - 1) / LUT_QUADS);
+#define TV_LUT_LAUNCH(C, K)                                                                                        \
+      do {                                                                                                         \
+        VCK(cudaFuncSetAttribute(tv_gather_lut_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                 (int)lut_smem));                                                                  \
+        tv_gather_lut_kernel<C, K><<<ctas, 32 * LUT_WARPS, lut_smem, ctx->stream>>>(g);                            \
+      } while (0)
+      if (p.curves) { if (lut_mode == 2) TV_LUT_LAUNCH(true, true); else TV_LUT_LAUNCH(true, false); }
+      else { if (lut_mode == 2) TV_LUT_LAUNCH(false, true); else TV_LUT_LAUNCH(false, false); }
+#undef TV_LUT_LAUNCH
+    } else {
 #define TV_LAUNCH1(E, C, P, S)                                                                            \
     do {                                                                                                  \
       VCK(cudaFuncSetAttribute(tv_gather_kernel<E, C, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -913,6 +1130,7 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
     }
 #undef TV_LAUNCH
 #undef TV_LAUNCH1
+    }
     VCK(cudaGetLastError());
     ctx->count_launch();
     if (overlap_d2h) {
