@@ -250,6 +250,33 @@ int visfd_cuda_vote_slab_host(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz
                               const visfd_membrane_params *p, float *out, float *tensor,
                               float *out_host);
 
+/* ---- clustering: LabelConnected ------------------------------------------------------ */
+/* lib/visfd/connect.hpp:171-1432 with the arguments HandleTV passes (bin/filter_mrc/handlers.cpp:1927-2034;
+ * `-connect`): connectivity 1, clusters grown from the saliency MAXIMA, the tensor positive
+ * definite near the target, clusters numbered from 1 by decreasing size, no must-link constraints, no voxel weights.
+ *   saliency  N floats; mask N floats or NULL (0 = ignore);
+ *   tensor    N*6 floats (flat xx,yy,zz,xy,yz,xz) or NULL (aaaafSymmetricTensor);
+ *   direction N*3 floats or NULL (aaaafVector AND aaaafVectorStandardized, which HandleTV aliases, :1985): read as the
+ *             voxels' directions unless direction_from_tensor != 0, in which case it is first filled with the principal
+ *             eigenvector of each tensor (handlers.cpp:1933-1950, eival_order); on return, with unsigned dot products,
+ *             it holds the sign-standardised directions (connect.hpp:698-722, :1080-1300).  NULL with a tensor: the
+ *             eigenvectors are computed internally and not returned.
+ *   thresholds as LabelConnected's arguments (cosines; -connect-angle, settings.cpp:175-178, :3075-3086).
+ *   labels    N int64: cluster number from 1, -1 = undefined; voxels outside the mask keep the reference's internal
+ *             marker n_maxima + 1 (connect.hpp:1398-1401 skips them; n_maxima is returned for that purpose).
+ *   cluster_maxima  optional, 3 floats (x,y,z) per cluster in label order, at most maxima_capacity clusters.
+ * Per-voxel tests and the six directed neighbour tests run on the GPU in one pass (16 flag bits per voxel); the
+ * priority-queue flood that assigns basins and merges clusters runs on the host in the reference's pop order over
+ * those flags (the basin numbering, the polarity of the standardised directions and the cut of non-orientable loops
+ * depend on that order).  The whole image must fit on one GPU (saliency 4 + tensor 24 + direction 12 + flags 2 B/voxel).
+ * DEVICE or HOST pointers (all image arrays on the same side; `labels` may be on either side). */
+int visfd_cuda_label_connected(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *saliency,
+                               const float *mask, const float *tensor, float *direction, int direction_from_tensor,
+                               int eival_order, int consider_dot_product_sign, float threshold_saliency,
+                               float threshold_vector_saliency, float threshold_vector_neighbor,
+                               float threshold_tensor_saliency, float threshold_tensor_neighbor, int64_t *labels,
+                               int64_t *n_clusters, float *cluster_maxima, int64_t maxima_capacity, int64_t *n_maxima);
+
 /* ---- bookkeeping for benchmarks (no reference counterpart) ------------------------- */
 /* Enable/disable the per-stage CUDA-event timing behind visfd_cuda_stage_ms. */
 void visfd_cuda_set_timing(visfd_ctx *ctx, int enabled);

@@ -218,7 +218,8 @@ class Oracle:
                                        _ptr(out))
         return dict(threshold=thr, hess_saliency=sal, direction=dire, tensor=tensor, out=out)
 
-    def label_connected(self, saliency, tensor, threshold_saliency, angle_deg=15.0, order=1, mask=None):
+    def label_connected(self, saliency, tensor, threshold_saliency, angle_deg=15.0, order=1, mask=None,
+                        want_direction=False, thresholds=None):
         """The clustering step of HandleTV (handlers.cpp:1927-2034 -> LabelConnected, connect.hpp:171), reference
         only: -> (labels int64, -1 undefined; number of clusters).  angle_deg as -connect-angle (settings.cpp:3075-3086)."""
         if self.kind != "reference":
@@ -228,10 +229,14 @@ class Oracle:
         mask = _f32(mask)
         labels = np.zeros(sal.shape, np.int64)
         c = float(np.float32(np.cos(angle_deg * np.pi / 180.0)))
+        tvs, tvn, tts, ttn = thresholds if thresholds is not None else (c, c, c, c)
         nz, ny, nx = sal.shape
+        dire = np.zeros(sal.shape + (3,), np.float32) if want_direction else None
         n = self._fn("label_connected", _i64)(_i(nx), _i(ny), _i(nz), _ptr(sal), _ptr(mask), _ptr(ten), _i(order),
-                                             _f(threshold_saliency), _f(c), _f(c), _f(c), _f(c),
-                                             labels.ctypes.data_as(C.c_void_p), None)
+                                             _f(threshold_saliency), _f(tvs), _f(tvn), _f(tts), _f(ttn),
+                                             labels.ctypes.data_as(C.c_void_p), _ptr(dire))
+        if want_direction:
+            return labels, int(n), dire
         return labels, int(n)
 
     # ---- thresholds ----------------------------------------------------------

@@ -336,6 +336,44 @@ class Context:
                                                   _ptr(dr)))
         return score, ev, dr
 
+    # ---- clustering --------------------------------------------------------------------------------
+    def label_connected(self, saliency, tensor, threshold_saliency, angle_deg=15.0, order=DECREASING_EIVALS,
+                        mask=None, direction=None, want_direction=False, consider_dot_product_sign=False,
+                        thresholds=None):
+        """LabelConnected as HandleTV calls it (connect.hpp:171, handlers.cpp:1927-2034; `-connect T -connect-angle A`).
+        -> dict(labels int64 [-1 undefined, clusters from 1 by decreasing size], n_clusters, n_maxima, maxima (n, 3),
+        direction (standardised; only if want_direction or direction was given)).  Arrays: numpy (host) only for
+        `labels`; inputs numpy or torch.  thresholds: (vector_saliency, vector_neighbor, tensor_saliency,
+        tensor_neighbor) cosines overriding angle_deg (settings.cpp:3075-3086 sets all four to cos(angle))."""
+        saliency, tensor, mask = _prep(saliency), _prep(tensor), _prep(mask)
+        shape = tuple(saliency.shape)
+        nz, ny, nx = shape
+        n = nz * ny * nx
+        c = float(np.float32(np.cos(angle_deg * np.pi / 180.0)))
+        tvs, tvn, tts, ttn = thresholds if thresholds is not None else (c, c, c, c)
+        from_tensor = 0
+        if direction is not None:
+            direction = _prep(direction)
+            if _is_torch(direction):
+                direction = direction.clone()
+            else:
+                direction = np.array(direction, dtype=np.float32, copy=True, order="C")
+        elif want_direction:
+            if tensor is None:
+                raise VisfdCudaError("want_direction needs a tensor or a direction field")
+            direction = _zeros(saliency, shape + (3,))
+            from_tensor = 1
+        labels = np.zeros(shape, np.int64)
+        ncl, nmax = _i64(), _i64()
+        cap = 1 << 16
+        maxima = np.zeros((cap, 3), np.float32)
+        self._ck(self.lib.visfd_cuda_label_connected(
+            self.h, _i64(nx), _i64(ny), _i64(nz), _ptr(saliency), _ptr(mask), _ptr(tensor), _ptr(direction),
+            _i(from_tensor), _i(order), _i(int(consider_dot_product_sign)), _f(threshold_saliency), _f(tvs), _f(tvn),
+            _f(tts), _f(ttn), labels.ctypes.data_as(C.c_void_p), C.byref(ncl), _ptr(maxima), _i64(cap), C.byref(nmax)))
+        return dict(labels=labels, n_clusters=ncl.value, n_maxima=nmax.value,
+                    maxima=maxima[:min(ncl.value, cap)].copy(), direction=direction)
+
     # ---- saliency cut ----------------------------------------------------------------------------
     def saliency_cut(self, sal, cut, is_fraction, mask=None):
         """handlers.cpp:1751-1797 -> (saliency after the cut, threshold)."""
