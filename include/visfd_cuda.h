@@ -114,6 +114,12 @@ int visfd_cuda_apply_dog(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
                          const float *src, float *dst, const float *mask,
                          const float sigma_a[3], const float sigma_b[3], const int hw[3],
                          float *A_out, float *B_out);
+/* filter_mrc's own ApplyDog (bin/filter_mrc/filter3d_variants.hpp:542-597, caller HandleDog handlers.cpp:309-320):
+ * each Gaussian with the half-width derived from its OWN sigma. */
+int visfd_cuda_apply_dog2(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
+                          const float *src, float *dst, const float *mask,
+                          const float sigma_a[3], const float sigma_b[3], const int hw_a[3],
+                          const int hw_b[3], float *A_out, float *B_out);
 /* ApplyLog<float>: lib/visfd/filter3d.hpp:1430-1507 */
 int visfd_cuda_apply_log(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
                          const float *src, float *dst, const float *mask,

@@ -220,10 +220,8 @@ class Oracle:
 
     def label_connected(self, saliency, tensor, threshold_saliency, angle_deg=15.0, order=1, mask=None,
                         want_direction=False, thresholds=None):
-        """The clustering step of HandleTV (handlers.cpp:1927-2034 -> LabelConnected, connect.hpp:171), reference
-        only: -> (labels int64, -1 undefined; number of clusters).  angle_deg as -connect-angle (settings.cpp:3075-3086)."""
-        if self.kind != "reference":
-            raise NotImplementedError("LabelConnected has no restatement yet (SURVEY 8f rank 1)")
+        """The clustering step of HandleTV (handlers.cpp:1927-2034 -> LabelConnected, connect.hpp:171), both
+        libraries: -> (labels int64, -1 undefined; number of clusters).  angle_deg as -connect-angle (settings.cpp:3075-3086)."""
         sal = _f32(saliency)
         ten = _f32(tensor)
         mask = _f32(mask)
@@ -232,7 +230,7 @@ class Oracle:
         tvs, tvn, tts, ttn = thresholds if thresholds is not None else (c, c, c, c)
         nz, ny, nx = sal.shape
         dire = np.zeros(sal.shape + (3,), np.float32) if want_direction else None
-        n = self._fn("label_connected", _i64)(_i(nx), _i(ny), _i(nz), _ptr(sal), _ptr(mask), _ptr(ten), _i(order),
+        n = self._fn("label_connected", _i64)(*self._dims(sal.shape), _ptr(sal), _ptr(mask), _ptr(ten), _i(order),
                                              _f(threshold_saliency), _f(tvs), _f(tvn), _f(tts), _f(ttn),
                                              labels.ctypes.data_as(C.c_void_p), _ptr(dire))
         if want_direction:

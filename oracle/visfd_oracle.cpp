@@ -5,7 +5,7 @@
 // function cites the reference file:line whose arithmetic it follows, including
 // the reference's mixed float/double/long double evaluation types, so that on
 // the same compiler/libm the results are bit-identical to oracle/_ref (the
-// reference itself); tests/test_oracle_vs_ref.py pins that, and the committed
+// reference itself); tests/test_oracle_golden.py pins that, and the committed
 // fixtures under tests/golden/ (generated from oracle/_ref by
 // tests/golden/make_golden.py) pin it where /root/reference is absent.
 //
@@ -25,6 +25,8 @@
 #include <cmath>
 #include <algorithm>
 #include <functional>
+#include <queue>
+#include <tuple>
 #include <vector>
 
 typedef int64_t i64;
@@ -1024,6 +1026,219 @@ void vo_blob_dog(i64 nx, i64 ny, i64 nz, const float *src, const float *mask,
     }
   *n_min = a;
   *n_max = b;
+}
+
+
+// ---------------------------------------------------------------------------
+// LabelConnected: lib/visfd/connect.hpp:171-1432 with the arguments HandleTV passes
+// (bin/filter_mrc/handlers.cpp:1927-2034): unsigned dot products, positive-definite
+// tensors, connectivity 1, maxima as seeds, clusters by size, no must-link constraints.
+// The voxels' directions are the first eigenvectors of the tensors
+// (handlers.cpp:1933-1950: ConvertFlatSym2Evects3, float Shoemake round trip included).
+// ---------------------------------------------------------------------------
+// TraceProductSym3 as COMPILED (lin3_utils.hpp:502-531): the reference indexes
+// MapIndices_linear_to_3x3 (a [6][2] table) with [i][j], i,j in 0..2, which walks the flat
+// table {0,0,1,1,2,2,...} and so only ever touches the diagonal entries 0,1,2:
+static float trace_product_sym3(const float *A, const float *B) {
+  return A[0] * B[0] + A[0] * B[1] + A[1] * B[2] + A[1] * B[0] + A[1] * B[1] + A[2] * B[2] + A[2] * B[1] +
+         A[2] * B[2] + A[0] * B[0];
+}
+static float frobenius_sym3(const float *A) { return std::sqrt(trace_product_sym3(A, A)); }
+static float dot3f(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+static void first_evec(const float m6[6], int order, float e0[3]) {   // eigen3_simple.hpp:392-405
+  float d6[6], ev[3], E[3][3];
+  vo_diagonalize_flat_sym3(m6, d6, order);
+  vo_diag_flat_to_evects(d6, ev, E);
+  e0[0] = E[0][0]; e0[1] = E[0][1]; e0[2] = E[0][2];
+}
+
+// labels: N int64 (cluster from 1, -1 undefined, n_maxima + 1 outside the mask: connect.hpp:1398-1401 skips
+// those voxels).  direction_out (optional N*3): the standardised directions.  Returns the number of clusters.
+i64 vo_label_connected(i64 nx, i64 ny, i64 nz, const float *sal, const float *mask, const float *tensor,
+                       int eival_order, float thr_sal, float thr_vs, float thr_vn, float thr_ts, float thr_tn,
+                       i64 *labels, float *direction_out) {
+  const i64 N = nx * ny * nz;
+  static const int nb[6][3] = {{0, 0, -1}, {0, -1, 0}, {-1, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};  // :212-240
+  if (thr_vs < 0) thr_vs = 0.0f;   // :190-205 (unsigned dot products)
+  if (thr_vn < 0) thr_vn = 0.0f;
+  std::vector<float> dir((size_t)N * 3, 0.0f);
+  for (i64 i = 0; i < N; i++) first_evec(tensor + 6 * i, eival_order, &dir[3 * i]);
+  auto masked = [&](i64 i) { return mask && mask[i] == 0.0f; };
+
+  // ---- _FindExtrema (morphology_implementation.hpp:57-515): maxima, plateaus, borders allowed ----
+  const float max_thr = (thr_sal == INFINITY) ? -INFINITY : thr_sal;   // :549-550
+  std::vector<i64> seed_voxel;
+  std::vector<float> seed_score;
+  {
+    std::vector<char> seen((size_t)N, 0);
+    std::vector<i64> q;
+    for (i64 i0 = 0; i0 < N; i0++) {
+      if (masked(i0) || seen[i0]) continue;
+      bool is_max = true;
+      q.assign(1, i0);
+      seen[i0] = 1;
+      for (size_t h = 0; h < q.size(); h++) {
+        const i64 v = q[h];
+        const i64 x = v % nx, y = (v / nx) % ny, z = v / (nx * ny);
+        for (int k = 0; k < 6; k++) {
+          const i64 jx = x + nb[k][0], jy = y + nb[k][1], jz = z + nb[k][2];
+          if (jx < 0 || jx >= nx || jy < 0 || jy >= ny || jz < 0 || jz >= nz) continue;
+          const i64 j = IDX(jx, jy, jz);
+          if (masked(j)) continue;
+          if (sal[j] == sal[v]) {
+            if (!seen[j]) { seen[j] = 1; q.push_back(j); }
+          } else if (sal[j] > sal[v]) {
+            is_max = false;
+          }
+        }
+      }
+      if (is_max && sal[i0] >= max_thr) { seed_voxel.push_back(i0); seed_score.push_back(sal[i0]); }
+    }
+    // sort(rbegin, rend) of (score, position): :449-470
+    std::vector<std::tuple<float, i64> > key(seed_voxel.size());
+    for (size_t k = 0; k < key.size(); k++) key[k] = std::make_tuple(seed_score[k], (i64)k);
+    std::sort(key.rbegin(), key.rend());
+    std::vector<i64> sv(key.size());
+    std::vector<float> ss(key.size());
+    for (size_t k = 0; k < key.size(); k++) { sv[k] = seed_voxel[std::get<1>(key[k])]; ss[k] = seed_score[std::get<1>(key[k])]; }
+    seed_voxel.swap(sv);
+    seed_score.swap(ss);
+  }
+  const i64 nb_ = (i64)seed_voxel.size();
+  const i64 UNDEFINED = nb_ + 1, QUEUED = nb_ + 2;
+  for (i64 i = 0; i < N; i++) labels[i] = UNDEFINED;
+  typedef std::tuple<float, i64, std::tuple<float, float, float> > Entry;   // lexicographic, like the reference's tuple
+  std::priority_queue<Entry> q;
+  for (i64 b = 0; b < nb_; b++) {
+    const i64 v = seed_voxel[b];
+    q.push(Entry(seed_score[b], b, std::make_tuple((float)(v % nx), (float)((v / nx) % ny), (float)(v / (nx * ny)))));
+    labels[v] = QUEUED;
+  }
+  std::vector<i64> basin2cluster(nb_);
+  std::vector<std::vector<i64> > cluster2basins(nb_);
+  for (i64 b = 0; b < nb_; b++) { basin2cluster[b] = b; cluster2basins[b].assign(1, b); }
+  std::vector<signed char> polarity(nb_, 1);
+
+  while (!q.empty()) {
+    const Entry e = q.top();
+    q.pop();
+    const float score = std::get<0>(e);
+    const float basin_f = (float)std::get<1>(e);   // Scalar i_which_basin, :438
+    const i64 basin = (i64)basin_f;
+    const i64 x = (i64)std::get<0>(std::get<2>(e)), y = (i64)std::get<1>(std::get<2>(e)), z = (i64)std::get<2>(std::get<2>(e));
+    const i64 i = IDX(x, y, z);
+    if (-score > thr_sal * -1.0f) { labels[i] = UNDEFINED; continue; }   // :445-449
+    if (masked(i)) { labels[i] = UNDEFINED; continue; }
+    {
+      // CalcHessianFiniteDifferences with the centre moved inside the image (visfd_utils.hpp:579-616), sign flipped (:487-492)
+      i64 cx = x, cy = y, cz = z;
+      if (cx == 0) cx++; else if (cx == nx - 1) cx--;
+      if (cy == 0) cy++; else if (cy == ny - 1) cy--;
+      if (cz == 0) cz++; else if (cz == nz - 1) cz--;
+      auto F = [&](int dx, int dy, int dz) { return sal[IDX(cx + dx, cy + dy, cz + dz)]; };
+      float h[6];
+      h[0] = (F(1, 0, 0) + F(-1, 0, 0) - 2 * F(0, 0, 0));
+      h[1] = (F(0, 1, 0) + F(0, -1, 0) - 2 * F(0, 0, 0));
+      h[2] = (F(0, 0, 1) + F(0, 0, -1) - 2 * F(0, 0, 0));
+      h[3] = 0.25 * (F(1, 1, 0) + F(-1, -1, 0) - F(1, -1, 0) - F(-1, 1, 0));
+      h[4] = 0.25 * (F(0, 1, 1) + F(0, -1, -1) - F(0, 1, -1) - F(0, -1, 1));
+      h[5] = 0.25 * (F(1, 0, 1) + F(-1, 0, -1) - F(-1, 0, 1) - F(1, 0, -1));
+      for (int k = 0; k < 6; k++) h[k] *= -1.0;
+      bool discard = false;
+      const float *T = tensor + 6 * i;
+      if (trace_product_sym3(h, T) < thr_ts * frobenius_sym3(h) * frobenius_sym3(T)) discard = true;   // :512-521
+      float e0[3];
+      first_evec(h, 1, e0);   // decreasing eigenvalues: clusters start at maxima (:173-177)
+      const float *V = &dir[3 * i];
+      const float d = dot3f(e0, V);
+      if (d * d < thr_vs * thr_vs * dot3f(e0, e0) * dot3f(V, V)) discard = true;   // :546-556
+      if (discard) {
+        labels[i] = UNDEFINED;
+        if (i == seed_voxel[basin]) basin2cluster[basin] = -1;   // :580-591
+        continue;
+      }
+    }
+    labels[i] = basin;
+    for (int k = 0; k < 6; k++) {
+      const i64 jx = x + nb[k][0], jy = y + nb[k][1], jz = z + nb[k][2];
+      if (jz < 0 || jz >= nz || jy < 0 || jy >= ny || jx < 0 || jx >= nx) continue;
+      const i64 j = IDX(jx, jy, jz);
+      if (masked(j)) continue;
+      const float *Ti = tensor + 6 * i, *Tj = tensor + 6 * j;
+      if (trace_product_sym3(Ti, Tj) < thr_tn * frobenius_sym3(Ti) * frobenius_sym3(Tj)) continue;   // :633-643
+      float *Vi = &dir[3 * i], *Vj = &dir[3 * j];
+      {
+        const float d = dot3f(Vi, Vj);
+        if (d * d < thr_vn * thr_vn * dot3f(Vi, Vi) * dot3f(Vj, Vj)) continue;   // :662-672
+      }
+      if (labels[j] == QUEUED) continue;
+      if (labels[j] == UNDEFINED) {
+        labels[j] = QUEUED;
+        q.push(Entry(sal[j], (i64)basin_f, std::make_tuple((float)jx, (float)jy, (float)jz)));
+        if (dot3f(Vi, Vj) < 0.0f) { Vj[0] *= -1.0f; Vj[1] *= -1.0f; Vj[2] *= -1.0f; }   // :698-722
+        continue;
+      }
+      const i64 bi = labels[i], bj = labels[j];
+      const i64 ci = basin2cluster[bi], cj = basin2cluster[bj];
+      const bool polarity_match = !(dot3f(Vi, Vj) * polarity[bi] * polarity[bj] < 0.0f);   // :735-748
+      if (ci == cj) continue;
+      const i64 keep = std::min(ci, cj), gone = std::max(ci, cj);
+      for (i64 b : cluster2basins[gone]) {
+        cluster2basins[keep].push_back(b);
+        basin2cluster[b] = keep;
+        if (!polarity_match) polarity[b] = (signed char)-polarity[b];
+      }
+      cluster2basins[gone].clear();
+    }
+  }
+  // ---- clusters (:1045-1068), polarity (:1080-1105), sizes, outward normals (:1183-1284), order by size (:1310-1355) ----
+  i64 n_clusters = 0;
+  std::vector<i64> old2new(nb_);
+  for (i64 b = 0; b < nb_; b++) {
+    old2new[b] = n_clusters;
+    if (basin2cluster[b] == b) n_clusters++;
+  }
+  for (i64 b = 0; b < nb_; b++)
+    if (basin2cluster[b] >= 0) basin2cluster[b] = old2new[basin2cluster[b]];
+  auto inside = [&](i64 i) { return !masked(i) && labels[i] != UNDEFINED; };
+  for (i64 i = 0; i < N; i++)
+    if (inside(i)) for (int d = 0; d < 3; d++) dir[3 * i + d] *= (float)polarity[labels[i]];
+  for (i64 i = 0; i < N; i++)
+    if (inside(i)) labels[i] = basin2cluster[labels[i]];
+  std::vector<long double> size(n_clusters, 0.0L), com(3 * n_clusters, 0.0L), sum(n_clusters, 0.0L);
+  for (i64 i = 0; i < N; i++)
+    if (inside(i)) {
+      size[labels[i]] += 1.0L;
+      com[3 * labels[i]] += i % nx; com[3 * labels[i] + 1] += (i / nx) % ny; com[3 * labels[i] + 2] += i / (nx * ny);
+    }
+  for (i64 c = 0; c < n_clusters; c++) for (int d = 0; d < 3; d++) com[3 * c + d] /= size[c];
+  for (i64 i = 0; i < N; i++)
+    if (inside(i)) {
+      const i64 c = labels[i];
+      float r[3];
+      r[0] = (i % nx) - com[3 * c]; r[1] = ((i / nx) % ny) - com[3 * c + 1]; r[2] = (i / (nx * ny)) - com[3 * c + 2];
+      long double delta = dot3f(r, &dir[3 * i]);
+      sum[c] += delta;
+    }
+  for (i64 i = 0; i < N; i++)
+    if (inside(i) && sum[labels[i]] < 0.0L) for (int d = 0; d < 3; d++) dir[3 * i + d] *= -1.0f;
+  {
+    std::vector<std::tuple<float, i64> > key(n_clusters);
+    for (i64 c = 0; c < n_clusters; c++) key[c] = std::make_tuple((float)size[c], c);
+    std::sort(key.rbegin(), key.rend());
+    std::vector<i64> rank(n_clusters);
+    for (i64 r = 0; r < n_clusters; r++) rank[std::get<1>(key[r])] = r;
+    for (i64 i = 0; i < N; i++)
+      if (inside(i)) labels[i] = rank[labels[i]];
+  }
+  for (i64 i = 0; i < N; i++) {
+    if (masked(i)) continue;
+    if (labels[i] == UNDEFINED) labels[i] = -1;
+    else labels[i] += 1;
+  }
+  if (direction_out) memcpy(direction_out, dir.data(), sizeof(float) * 3 * (size_t)N);
+  return n_clusters;
 }
 
 } // extern "C"

@@ -237,3 +237,55 @@ def test_label_connected_hook_reproduces_the_cli(ref_oracle, golden):
     cli = golden["c1_connect_labels"]
     assert np.array_equal(labels == 1, cli == 1) and int((labels == 1).sum()) == 69
     assert np.array_equal(labels == -1, cli == 2)          # undefined voxels: max label + 1 in the file
+
+
+def _random_connect_case(oracle, seed, shape=(18, 20, 22)):
+    rng = np.random.default_rng(500 + seed)
+    smooth = lambda a: oracle.apply_gauss(a.astype(np.float32), 1.5, 4)[0]
+    sal = smooth(rng.standard_normal(shape))
+    sal = (sal - sal.min()).astype(np.float32)
+    if seed % 3 == 2:                       # plateaus
+        sal = np.round(sal / sal.max() * 10.0).astype(np.float32)
+    n = np.stack([smooth(rng.standard_normal(shape)) for _ in range(3)], axis=-1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True) + 1e-12
+    T = np.stack([n[..., 0] ** 2, n[..., 1] ** 2, n[..., 2] ** 2, n[..., 0] * n[..., 1], n[..., 1] * n[..., 2],
+                  n[..., 0] * n[..., 2]], axis=-1) * rng.uniform(0.5, 2.0, shape)[..., None]
+    T[..., :3] += 0.05 + 0.02 * rng.standard_normal(shape + (3,))
+    mask = (rng.random(shape) > 0.15).astype(np.float32) if seed % 2 else None
+    return sal, T.astype(np.float32), mask, float(np.quantile(sal, 0.6))
+
+
+def test_label_connected_restatement_is_the_reference(oracle, ref_oracle, golden):
+    """oracle/visfd_oracle.cpp::vo_label_connected == the unmodified LabelConnected (lib/visfd/connect.hpp:171) behind
+    HandleTV's arguments, label for label and direction for direction (bit-identical: same compiler, same libm), on
+    the C1 pipeline output and on random fields with masks, plateaus, rejected seeds and merges."""
+    sigma, ratio, tv_sigma, expo, cutoff, best = [float(v) for v in golden["c1_params"]]
+    r = ref_oracle.membrane(golden["c1_in_binned"], sigma, ratio, 1, best, True, tv_sigma, int(expo), cutoff)
+    a = oracle.label_connected(r["out"], r["tensor"], 1e9, angle_deg=30.0, want_direction=True)
+    b = ref_oracle.label_connected(r["out"], r["tensor"], 1e9, angle_deg=30.0, want_direction=True)
+    assert a[1] == b[1] == 1 and np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    total = 0
+    for seed in range(6):
+        sal, T, mask, thr = _random_connect_case(oracle, seed)
+        for angle in (25.0, 60.0):
+            a = oracle.label_connected(sal, T, thr, angle_deg=angle, mask=mask, want_direction=True)
+            b = ref_oracle.label_connected(sal, T, thr, angle_deg=angle, mask=mask, want_direction=True)
+            assert a[1] == b[1]
+            assert np.array_equal(a[0], b[0])
+            assert np.array_equal(a[2], b[2])
+            total += a[1]
+    assert total > 20
+    ninf = -np.inf
+    sal, T, mask, thr = _random_connect_case(oracle, 2)
+    a = oracle.label_connected(sal, T, 6.0, thresholds=(ninf,) * 4)
+    b = ref_oracle.label_connected(sal, T, 6.0, thresholds=(ninf,) * 4)
+    assert a[1] == b[1] > 1 and np.array_equal(a[0], b[0])
+
+
+def test_label_connected_restatement_c1_known_answer(oracle, golden):
+    """Without the reference tree: the restatement on the C1 pipeline (restated too) gives the stock binary's pass 2."""
+    sigma, ratio, tv_sigma, expo, cutoff, best = [float(v) for v in golden["c1_params"]]
+    r = oracle.membrane(golden["c1_in_binned"], sigma, ratio, 1, best, True, tv_sigma, int(expo), cutoff)
+    labels, n = oracle.label_connected(r["out"], r["tensor"], 1e9, angle_deg=30.0)
+    cli = golden["c1_connect_labels"]
+    assert n == 1 and np.array_equal(labels == 1, cli == 1) and np.array_equal(labels == -1, cli == 2)

@@ -111,6 +111,20 @@ int visfd_cuda_apply_dog(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, con
   API_END(ctx)
 }
 
+int visfd_cuda_apply_dog2(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src, float *dst,
+                          const float *mask, const float sigma_a[3], const float sigma_b[3], const int hw_a[3],
+                          const int hw_b[3], float *A_out, float *B_out) {
+  API_BEGIN(ctx)
+  check_dims(nx, ny, nz);
+  VREQUIRE(src && dst && sigma_a && sigma_b && hw_a && hw_b, "NULL argument");
+  const size_t N = (size_t)nx * ny * nz;
+  const bool host = on_host(src);
+  Staged<float> s(ctx, src, N, Dir::In, host), m(ctx, mask, N, Dir::In, host), d(ctx, dst, N, Dir::Out, host);
+  dog_device(ctx, nx, ny, nz, 0, nz, s.get(), d.get(), m.get(), sigma_a, sigma_b, hw_a, 1.0f, A_out, B_out, hw_b);
+  d.finish();
+  API_END(ctx)
+}
+
 int visfd_cuda_apply_log_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz_local, int64_t z_offset,
                               int64_t nz_global, const float *src, float *dst, const float *mask,
                               const float sigma[3], float delta, float truncate_ratio, float *A_out,

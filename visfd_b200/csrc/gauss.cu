@@ -1113,12 +1113,12 @@ float gauss_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i
 // ApplyDog (filter3d.hpp:1340-1402): dst = G_a(src) - G_b(src), optionally * scale (ApplyLog).
 void dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
                 const float *src, float *dst, const float *mask, const float sigma_a[3],
-                const float sigma_b[3], const int hw[3], float scale, float *A, float *B) {
+                const float sigma_b[3], const int hw[3], float scale, float *A, float *B, const int *hw_b) {
   const i64 N = nx * ny * nz_local;
   Scratch<float> ga(ctx, N);
   float a = gauss_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, ga.get(), mask, sigma_a, hw,
                          true, nullptr, 1.0f);
-  float b = gauss_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, dst, mask, sigma_b, hw, true,
+  float b = gauss_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, dst, mask, sigma_b, hw_b ? hw_b : hw, true,
                          ga.get(), scale);
   if (A) *A = a;
   if (B) *B = b;

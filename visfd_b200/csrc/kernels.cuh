@@ -18,7 +18,8 @@ float gauss_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i
                    float combine_scale);
 void dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
                 const float *src, float *dst, const float *mask, const float sigma_a[3],
-                const float sigma_b[3], const int hw[3], float scale, float *A, float *B);
+                const float sigma_b[3], const int hw[3], float scale, float *A, float *B,
+                const int *hw_b = nullptr /* half-width of the second Gaussian if it differs (filter_mrc's -dog) */);
 void log_params(const float sigma[3], float delta, float truncate_ratio, float sigma_a[3],
                 float sigma_b[3], int hw[3], float *scale);
 void fill_device(visfd_ctx *ctx, float *p, float v, i64 n);

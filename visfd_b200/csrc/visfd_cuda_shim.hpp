@@ -191,6 +191,32 @@ inline void ApplyLog(const int image_size[3], float const *const *const *aaafSou
   d.commit();
 }
 
+
+// filter_mrc's variants with (truncate_ratio, truncate_threshold): bin/filter_mrc/filter3d_variants.hpp:542-597, :603-634
+inline void ApplyDog(const int image_size[3], float const *const *const *aaafSource, float ***aaafDest,
+                     float const *const *const *aaafMask, const float sigma_a[3], const float sigma_b[3],
+                     float filter_truncate_ratio, float filter_truncate_threshold, float *pA = nullptr,
+                     float *pB = nullptr, std::ostream *pReportProgress = nullptr) {
+  (void)pReportProgress;
+  int hwa[3], hwb[3];   // each Gaussian keeps the half-width of its own sigma (two ApplyGauss calls in the reference)
+  for (int d = 0; d < 3; d++) {
+    hwa[d] = visfd_cuda_gauss_halfwidth(sigma_a[d], filter_truncate_ratio, filter_truncate_threshold);
+    hwb[d] = visfd_cuda_gauss_halfwidth(sigma_b[d], filter_truncate_ratio, filter_truncate_threshold);
+  }
+  Dense3<float, 1> s(image_size, aaafSource, false), m(image_size, aaafMask, false), d(image_size, aaafDest, true);
+  Check(visfd_cuda_apply_dog2(Context(), image_size[0], image_size[1], image_size[2], s.data(), d.data(), m.data(),
+                              sigma_a, sigma_b, hwa, hwb, pA, pB));
+  d.commit();
+}
+inline void ApplyLog(const int image_size[3], float const *const *const *aaafSource, float ***aaafDest,
+                     float const *const *const *aaafMask, const float sigma[3], float delta_sigma_over_sigma,
+                     float filter_truncate_ratio, float filter_truncate_threshold, float *pA = nullptr,
+                     float *pB = nullptr, std::ostream *pReportProgress = nullptr) {
+  if (filter_truncate_ratio < 0) filter_truncate_ratio = std::sqrt(-2 * std::log(filter_truncate_threshold));
+  ApplyLog(image_size, aaafSource, aaafDest, aaafMask, sigma, delta_sigma_over_sigma, filter_truncate_ratio, pA, pB,
+           pReportProgress);
+}
+
 // ---- features (lib/visfd/feature.hpp) ---------------------------------------------------------
 // CalcHessian<float, array<float,3>, float*>: feature.hpp:1210-1348
 inline void CalcHessian(int const image_size[3], float const *const *const *aaafSource,
@@ -249,6 +275,103 @@ inline void BlobDog(int const image_size[3], float const *const *const *aaafSour
   };
   emit(nmin, mc, ms, msc, pva_minima_crds, pv_minima_sigma, pv_minima_scores);
   emit(nmax, xc, xs, xsc, pva_maxima_crds, pv_maxima_sigma, pv_maxima_scores);
+}
+
+
+// BlobDogD<float>: feature.hpp:449-512 (diameters instead of sigmas: sigma = diameter / (2 sqrt 3))
+inline void BlobDogD(int const image_size[3], float const *const *const *aaafSource,
+                     float const *const *const *aaafMask, const std::vector<float> &blob_diameters,
+                     std::vector<std::array<float, 3> > *pva_minima_crds = nullptr,
+                     std::vector<std::array<float, 3> > *pva_maxima_crds = nullptr,
+                     std::vector<float> *pv_minima_diameters = nullptr, std::vector<float> *pv_maxima_diameters = nullptr,
+                     std::vector<float> *pv_minima_scores = nullptr, std::vector<float> *pv_maxima_scores = nullptr,
+                     const float aspect_ratio[3] = nullptr, float delta_sigma_over_sigma = 0.02,
+                     float truncate_ratio = 2.5, float minima_threshold = std::numeric_limits<float>::infinity(),
+                     float maxima_threshold = -std::numeric_limits<float>::infinity(),
+                     bool use_threshold_ratios = false, std::ostream *pReportProgress = nullptr,
+                     float ****aaaafI = nullptr) {
+  std::vector<float> minima_sigma, maxima_sigma, blob_sigma(blob_diameters.size());
+  for (size_t i = 0; i < blob_diameters.size(); i++) blob_sigma[i] = blob_diameters[i] / (2.0 * std::sqrt(3));
+  BlobDog(image_size, aaafSource, aaafMask, blob_sigma, pva_minima_crds, pva_maxima_crds, &minima_sigma, &maxima_sigma,
+          pv_minima_scores, pv_maxima_scores, aspect_ratio, delta_sigma_over_sigma, truncate_ratio, minima_threshold,
+          maxima_threshold, use_threshold_ratios, pReportProgress, aaaafI);
+  if (pv_minima_diameters) {
+    pv_minima_diameters->resize(minima_sigma.size());
+    for (size_t i = 0; i < minima_sigma.size(); i++) (*pv_minima_diameters)[i] = minima_sigma[i] * 2.0 * std::sqrt(3);
+  }
+  if (pv_maxima_diameters) {
+    pv_maxima_diameters->resize(maxima_sigma.size());
+    for (size_t i = 0; i < maxima_sigma.size(); i++) (*pv_maxima_diameters)[i] = maxima_sigma[i] * 2.0 * std::sqrt(3);
+  }
+}
+
+// LabelConnected<float, ptrdiff_t, float, array<float,3>, float*>: lib/visfd/connect.hpp:171-1432 with the argument
+// list of the reference (the values HandleTV and HandleLabelConnected pass, handlers.cpp:1963-1993, :1438-1470).
+// Supported: connectivity 1, clusters grown from maxima, sorted by size, no voxel weights, no must-link
+// constraints; aaaafVectorStandardized must be nullptr or alias aaaafVector (as in HandleTV).  Anything else throws.
+inline size_t LabelConnected(const int image_size[3], float const *const *const *aaafSaliency, ptrdiff_t ***aaaiDest,
+                             float const *const *const *aaafMask,
+                             float threshold_saliency = -std::numeric_limits<float>::infinity(),
+                             std::array<float, 3> const *const *const *aaaafVector = nullptr,
+                             float threshold_vector_saliency = -std::numeric_limits<float>::infinity(),
+                             float threshold_vector_neighbor = -std::numeric_limits<float>::infinity(),
+                             bool consider_dot_product_sign = true, float *const *const *const *aaaafSymmetricTensor = nullptr,
+                             float threshold_tensor_saliency = -std::numeric_limits<float>::infinity(),
+                             float threshold_tensor_neighbor = -std::numeric_limits<float>::infinity(),
+                             bool tensor_is_positive_definite_near_target = true, int connectivity = 1,
+                             ptrdiff_t label_undefined = -1,
+                             std::vector<std::array<float, 3> > *pv_cluster_maxima = nullptr,
+                             std::vector<float> *pv_cluster_sizes = nullptr,
+                             std::vector<float> *pv_cluster_saliencies = nullptr, int sort_criteria = 1 /*SORT_BY_SIZE*/,
+                             float const *const *const *aaafVoxelWeights = nullptr,
+                             std::array<float, 3> ***aaaafVectorStandardized = nullptr,
+                             const void *pMustLinkConstraints = nullptr, const void *pMustLinkDirections = nullptr,
+                             bool start_from_saliency_maxima = true, std::ostream *pReportProgress = nullptr) {
+  if (connectivity != 1 || !tensor_is_positive_definite_near_target || !start_from_saliency_maxima ||
+      sort_criteria != 1 || aaafVoxelWeights || pMustLinkConstraints)
+    throw VisfdErr("Error: the CUDA LabelConnected supports connectivity 1, maxima seeds, size ordering, no weights and "
+                   "no must-link constraints\n");
+  (void)pMustLinkDirections;   // only read together with the constraints (connect.hpp:946-961); HandleTV passes an empty list
+  if (aaaafVectorStandardized && (std::array<float, 3> const *const *const *)aaaafVectorStandardized != aaaafVector)
+    throw VisfdErr("Error: the CUDA LabelConnected standardises the direction array in place\n");
+  if (aaaafSymmetricTensor && !aaaafVector)
+    throw VisfdErr("Error: LabelConnected with tensors needs the direction array as well (connect.hpp:648-676)\n");
+  Dense3<float, 1> sal(image_size, aaafSaliency, false), m(image_size, aaafMask, false);
+  Dense3<std::array<float, 3>, 3> v(image_size, aaaafVector, aaaafVectorStandardized != nullptr);
+  DenseTensor t(image_size, const_cast<float ****>(aaaafSymmetricTensor), 6, true);
+  const size_t N = (size_t)image_size[0] * image_size[1] * image_size[2];
+  std::vector<int64_t> lab(N);
+  int64_t n_clusters = 0, n_maxima = 0;
+  std::vector<float> maxima(3 * (size_t)(1 << 20));
+  // a caller that does not want standardised directions must not see its array change: work on a copy
+  std::vector<float> vcopy;
+  float *vptr = v.data();
+  if (vptr && !aaaafVectorStandardized) {
+    vcopy.assign(vptr, vptr + 3 * N);
+    vptr = vcopy.data();
+  }
+  Check(visfd_cuda_label_connected(Context(), image_size[0], image_size[1], image_size[2], sal.data(), m.data(), t.data(),
+                                   vptr, 0, VISFD_DECREASING_EIVALS, consider_dot_product_sign ? 1 : 0,
+                                   threshold_saliency, threshold_vector_saliency, threshold_vector_neighbor,
+                                   threshold_tensor_saliency, threshold_tensor_neighbor, lab.data(), &n_clusters,
+                                   maxima.data(), (int64_t)(maxima.size() / 3), &n_maxima));
+  v.commit();
+  const size_t nx = image_size[0], ny = image_size[1], nz = image_size[2];
+  for (size_t iz = 0; iz < nz; iz++)
+    for (size_t iy = 0; iy < ny; iy++)
+      for (size_t ix = 0; ix < nx; ix++) {
+        const int64_t l = lab[(iz * ny + iy) * nx + ix];
+        aaaiDest[iz][iy][ix] = (l == -1) ? label_undefined : (ptrdiff_t)l;
+      }
+  if (pv_cluster_maxima) {
+    pv_cluster_maxima->resize((size_t)n_clusters);
+    for (size_t c = 0; c < (size_t)n_clusters && 3 * c + 2 < maxima.size(); c++)
+      (*pv_cluster_maxima)[c] = {maxima[3 * c], maxima[3 * c + 1], maxima[3 * c + 2]};
+  }
+  if (pv_cluster_sizes) pv_cluster_sizes->clear();            // not reported (HandleTV does not read them)
+  if (pv_cluster_saliencies) pv_cluster_saliencies->clear();
+  if (pReportProgress) *pReportProgress << "Number of clusters found: " << n_clusters << "\n";
+  return (size_t)n_clusters;
 }
 
 // TV3D<float, int, array<float,3>, float*>: feature.hpp:1631-2483
