@@ -109,6 +109,8 @@ int visfd_cuda_apply_gauss_slab(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t 
                                 int64_t z_offset, int64_t nz_global, const float *src,
                                 float *dst, const float *mask, const float sigma[3],
                                 const int hw[3], int normalize, float *A_out);
+/* (All separable filters: with DEVICE pointers dst must not alias src or mask -- the call fails otherwise;
+ * host arrays are staged through separate device buffers and may alias as in the reference.) */
 /* ApplyDog<float>: lib/visfd/filter3d.hpp:1340-1402 */
 int visfd_cuda_apply_dog(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
                          const float *src, float *dst, const float *mask,

@@ -104,7 +104,7 @@ def _pack_blobs(c, s, sc, n):
 
 
 def blob_finalize(minima, maxima, best, minima_threshold=np.inf, maxima_threshold=-np.inf,
-                  use_threshold_ratios=True, lib=None):
+                  use_threshold_ratios=False, lib=None):
     """The final score filter of BlobDog on (n, 5) candidate rows x,y,z,sigma,score (host only, no GPU)."""
     lib = lib or load_library()
     out, cols, counts = [], [], []
@@ -534,7 +534,7 @@ class Context:
 
     # ---- blobs -----------------------------------------------------------------------------------------------------
     def blob_dog(self, src, sigmas, delta=0.02, truncate_ratio=2.5, mask=None, minima_threshold=np.inf,
-                 maxima_threshold=-np.inf, use_threshold_ratios=True, capacity=1 << 20):
+                 maxima_threshold=-np.inf, use_threshold_ratios=False, capacity=1 << 20):
         """BlobDog (lib/visfd/feature.hpp:56-427) -> (minima, maxima) rows of x,y,z,sigma,score."""
         src, mask = _prep(src), _prep(mask)
         sg = np.ascontiguousarray(np.asarray(sigmas), np.float32)
@@ -546,11 +546,14 @@ class Context:
                                               _f(maxima_threshold), _i(int(use_threshold_ratios)), _i64(capacity),
                                               _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]), C.byref(nmin),
                                               _ptr(bufs[3]), _ptr(bufs[4]), _ptr(bufs[5]), C.byref(nmax)))
-        a, b = min(nmin.value, capacity), min(nmax.value, capacity)
-        return _pack_blobs(bufs[0], bufs[1], bufs[2], a), _pack_blobs(bufs[3], bufs[4], bufs[5], b)
+        if nmin.value > capacity or nmax.value > capacity:
+            raise VisfdCudaError("blob_dog: %d minima / %d maxima exceed the capacity of %d rows; call again with a "
+                                 "larger capacity" % (nmin.value, nmax.value, capacity))
+        return (_pack_blobs(bufs[0], bufs[1], bufs[2], nmin.value),
+                _pack_blobs(bufs[3], bufs[4], bufs[5], nmax.value))
 
     def blob_dog_slab(self, src, z_offset, nz_global, own, sigmas, delta=0.02, truncate_ratio=2.5, mask=None,
-                      minima_threshold=np.inf, maxima_threshold=-np.inf, use_threshold_ratios=True,
+                      minima_threshold=np.inf, maxima_threshold=-np.inf, use_threshold_ratios=False,
                       capacity=1 << 20):
         """visfd_cuda_blob_dog_slab: BlobDog on a z-slab (device tensor; own = slab-local receiver planes).
         -> (minima, maxima, (best_min, best_max)): candidate rows x,y,z(image),sigma,score BEFORE the final
@@ -574,7 +577,7 @@ class Context:
                 (best[0], best[1]))
 
     def blob_finalize(self, minima, maxima, best, minima_threshold=np.inf, maxima_threshold=-np.inf,
-                      use_threshold_ratios=True):
+                      use_threshold_ratios=False):
         """visfd_cuda_blob_finalize: the final score filter (feature.hpp:362-417) on gathered candidate rows,
         given the best scores of the whole image."""
         return blob_finalize(minima, maxima, best, minima_threshold, maxima_threshold, use_threshold_ratios, self.lib)

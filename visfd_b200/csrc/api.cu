@@ -301,16 +301,16 @@ static bool upload_smooth_ridge_chunked(visfd_ctx *ctx, int64_t nx, int64_t ny, 
   float *stage[2] = {stage0.get(), stage1.get()};
   if (!ctx->copy_stream) VCK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   const int n_chunks = (int)((nz + cz - 1) / cz);
+  EventList events(ctx);   // declared after the staging slabs: drained and destroyed before they return to the pool
   std::vector<cudaEvent_t> uploaded((size_t)n_chunks), consumed((size_t)n_chunks);
   for (int c = 0; c < n_chunks; c++) {
-    VCK(cudaEventCreateWithFlags(&uploaded[(size_t)c], cudaEventDisableTiming));
-    VCK(cudaEventCreateWithFlags(&consumed[(size_t)c], cudaEventDisableTiming));
+    uploaded[(size_t)c] = events.add();
+    consumed[(size_t)c] = events.add();
   }
   const float sg[3] = {p->sigma, p->sigma, p->sigma};
   const int hw[3] = {h, h, h};
   // the staging slabs come from the stream-ordered pool: whatever used them last ran on ctx->stream
-  cudaEvent_t start;
-  VCK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+  cudaEvent_t start = events.add();
   VCK(cudaEventRecord(start, ctx->stream));
   VCK(cudaStreamWaitEvent(ctx->copy_stream, start, 0));
   for (int c = 0; c < n_chunks; c++) {
@@ -332,11 +332,6 @@ static bool upload_smooth_ridge_chunked(visfd_ctx *ctx, int64_t nx, int64_t ny, 
   }
   VCK(cudaStreamSynchronize(ctx->copy_stream));
   VCK(cudaStreamSynchronize(ctx->stream));   // before the staging slabs go back to the pool
-  for (int c = 0; c < n_chunks; c++) {
-    cudaEventDestroy(uploaded[(size_t)c]);
-    cudaEventDestroy(consumed[(size_t)c]);
-  }
-  cudaEventDestroy(start);
   return true;
 }
 

@@ -105,6 +105,28 @@ void reset_stage_times(visfd_ctx *ctx);
 void drop_pending_stage_events(visfd_ctx *ctx);
 void resolve_stage_times(visfd_ctx *ctx);  // call after stream sync
 
+// CUDA events with a guaranteed end of life: on scope exit (normal or by exception) both streams of the
+// context are drained first, so that copies still in flight on copy_stream cannot write into staging blocks
+// the pool has already handed to someone else, and then the events are destroyed.
+struct EventList {
+  visfd_ctx *ctx;
+  std::vector<cudaEvent_t> ev;
+  explicit EventList(visfd_ctx *c) : ctx(c) {}
+  cudaEvent_t add() {
+    cudaEvent_t e;
+    VCK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev.push_back(e);
+    return e;
+  }
+  ~EventList() {
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+  EventList(const EventList &) = delete;
+  EventList &operator=(const EventList &) = delete;
+};
+
 // A user array that may live on the host or on the device.
 enum class Dir { In, Out, InOut };
 template <typename T>

@@ -7,14 +7,14 @@
 // :1493-1498) are fused into the X sweep's epilogue, so they cost no extra pass.
 //
 // Kernels
-//  sweep_axis_kernel : Y or Z sweep.  Lanes run along x (float4 per lane, 512 B
-//      coalesced per warp row); a CTA stages (64 + 2hw) rows of 128 columns in
-//      shared memory once and every thread produces 8 consecutive outputs along
-//      the sweep axis for its 4 columns from registers (32 accumulators), so a
-//      shared-memory value is read once per thread and used for 8 FMAs x 4 lanes.
-//  sweep_x_kernel    : X sweep.  A CTA stages 32 row segments of 128 + 2hw columns;
-//      every thread produces 4 consecutive x outputs for 4 rows (16 accumulators),
-//      reading shared memory as conflict-free float4.
+//  sweep_axis3_kernel : Y or Z sweep, the default.  A CTA owns 128 columns x 96 outputs along the axis in 3 chunks;
+//      the whole tile is requested up front by TMA (cp.async.bulk.tensor boxes of 8 rows, zero-filled outside the
+//      volume, one mbarrier per chunk); tap-stationary compute: a thread keeps a window of 8 input rows in registers
+//      and produces 4 outputs x float4 with every tap useful.
+//  sweep_x2_kernel    : X sweep, the default.  64 rows x (128 + 2 hw) columns by TMA in two chunks; first / last tap
+//      steps specialised on hw mod 4; normalisation and DoG / LoG combine in the epilogue.
+//  sweep_axis2_kernel / sweep_axis_kernel / sweep_x_kernel : fall-backs for ragged nx (no float4 / TMA alignment),
+//      very wide filters, and masks (sweep_axis_kernel<EXACT_MASKED>: (h*m)*f per tap from two shared-memory tiles).
 // Out-of-volume taps are zero (the reference skips them, filter1d.hpp:98-99); the
 // renormalisation divides by the product of the three 1-D edge profiles.
 //
@@ -868,11 +868,8 @@ static void launch_axis_mode(visfd_ctx *ctx, const float *in, float *out, const 
                  (2 * hw + 1 + TAP_PAD_LO + TAP_PAD_HI)) * sizeof(float);
   VREQUIRE(smem <= 220 * 1024, "filter half-width too large for the sweep kernel");
   VREQUIRE(n_other <= 65535 && div_up(n_axis, AX_TA) <= 65535, "volume too large in y/z for one launch");
-  static bool attr_set = false;
-  if (!attr_set) {
-    VCK(cudaFuncSetAttribute(sweep_axis_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
+  // per launch: the attribute is per DEVICE and a process may hold contexts on several GPUs
+  VCK(cudaFuncSetAttribute(sweep_axis_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0) &&
                (!mask || ((uintptr_t)mask & 15) == 0);
   dim3 grid(div_up(nx, AX_TX), div_up(n_axis, AX_TA), (unsigned)n_other);
@@ -890,11 +887,8 @@ static void launch_axis2_mode(visfd_ctx *ctx, const float *in, float *out, const
   const size_t smem = ((size_t)(ntap8 + A2_S - 1) * AX_TX + ntap8) * sizeof(float);
   VREQUIRE(smem <= 220 * 1024, "filter half-width too large for the sweep kernel");
   VREQUIRE(n_other <= 65535 && div_up(n_axis, A2_S) <= 65535, "volume too large in y/z for one launch");
-  static bool attr_set = false;
-  if (!attr_set) {
-    VCK(cudaFuncSetAttribute(sweep_axis2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
+  // per launch: the attribute is per DEVICE and a process may hold contexts on several GPUs
+  VCK(cudaFuncSetAttribute(sweep_axis2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
   dim3 grid(div_up(nx, AX_TX), div_up(n_axis, A2_S), (unsigned)n_other);
   dim3 block(32, 8);
@@ -911,12 +905,9 @@ static bool launch_axis3_mode(visfd_ctx *ctx, const float *in, float *out, const
   const size_t smem = ((size_t)(ntap8 + A3_NCH * A2_S) * AX_TX + ntap8) * sizeof(float) + A3_NCH * sizeof(uint64_t);
   const bool vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
   if (!vec_ok || smem > 100 * 1024 || ntap8 > 256 || n_other > 65535 || div_up(n_axis, A3_NCH * A2_S) > 65535) return false;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
-  }
+  // per launch: the attribute is per DEVICE and a process may hold contexts on several GPUs
+  VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   dim3 grid(div_up(nx, AX_TX), div_up(n_axis, A3_NCH * A2_S), (unsigned)n_other);
   dim3 block(32, 8);
   // the volume as a 3-D tensor (x, y, z): Y sweep: s_axis == nx; Z sweep: s_other == nx
@@ -962,12 +953,9 @@ static void launch_x(visfd_ctx *ctx, const float *in, float *out, const float *d
   const int pitch = XS_TX + 2 * hwpad + 4;
   size_t smem = ((size_t)XS_ROWS * pitch + (2 * hw + 1 + TAP_PAD_LO + TAP_PAD_HI)) * sizeof(float);
   VREQUIRE(smem <= 220 * 1024, "filter half-width too large for the x sweep kernel");
-  static bool attr_set = false;
-  if (!attr_set) {
-    VCK(cudaFuncSetAttribute(sweep_x_kernel<MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    VCK(cudaFuncSetAttribute(sweep_x_kernel<MODE_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
+  // per launch: the attribute is per DEVICE and a process may hold contexts on several GPUs
+  VCK(cudaFuncSetAttribute(sweep_x_kernel<MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  VCK(cudaFuncSetAttribute(sweep_x_kernel<MODE_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0) &&
                (!ep.den3 || ((uintptr_t)ep.den3 & 15) == 0) && (!ep.minuend || ((uintptr_t)ep.minuend & 15) == 0);
   {
@@ -1041,6 +1029,10 @@ float separable_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offse
   VREQUIRE(nx > 0 && ny > 0 && nz_local > 0, "empty volume");
   VREQUIRE(hw[0] >= 0 && hw[1] >= 0 && hw[2] >= 0, "negative filter half-width");
   VREQUIRE(z_offset >= 0 && z_offset + nz_local <= nz_global, "slab outside the volume");
+  // The Z sweep reads src while other CTAs already write dst: unlike the reference (one temporary per line,
+  // filter3d.hpp:710-713 copies first) the device path cannot filter in place
+  VREQUIRE(src != dst && (!mask || mask != dst) && (!combine_minuend || combine_minuend != dst),
+           "separable filter: dst must not alias src, mask or the minuend (device pointers)");
   // upload taps (+ edge profiles) in one host buffer
   const int nt[3] = {2 * hw[0] + 1, 2 * hw[1] + 1, 2 * hw[2] + 1};
   const i64 n_dim[3] = {nx, ny, nz_local};

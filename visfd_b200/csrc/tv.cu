@@ -922,6 +922,7 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   VREQUIRE(nx > 0 && ny > 0 && nz_local > 0, "empty volume");
   VREQUIRE(own_z0 >= 0 && own_z1 <= nz_local && own_z0 <= own_z1, "receiver planes outside the slab");
   VREQUIRE(p.sigma > 0.0f, "tensor-voting sigma must be positive");
+  VREQUIRE(p.exponent >= 1, "tensor-voting angle exponent must be >= 1");
   VREQUIRE(direction || smoothed, "tensor voting needs voter directions");
   const int hw = tv_halfwidth(p.sigma, p.cutoff_ratio);
   VREQUIRE(hw >= 0 && hw <= TV_MAX_REACH * BR, "tensor-voting radius too large (max 56 voxels)");
@@ -1023,7 +1024,8 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   const int n_chunks = (int)((planes + chunk_planes - 1) / chunk_planes);
   VREQUIRE((i64)g.ntx * g.nty * div_up(chunk_planes, TV_TILE_Z) * 4 / TV_WARPS < 2147483647LL,
            "too many receiver tiles for one launch");
-  std::vector<cudaEvent_t> chunk_done;
+  EventList chunk_events(ctx);
+  std::vector<cudaEvent_t> &chunk_done = chunk_events.ev;
   // ---- table kernel set-up ---------------------------------------------------------------------
   const size_t per_warp = (TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t) + 15) & ~(size_t)15;
   Scratch<float2> lut;
@@ -1134,10 +1136,7 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
     VCK(cudaGetLastError());
     ctx->count_launch();
     if (overlap_d2h) {
-      cudaEvent_t ev;
-      VCK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      VCK(cudaEventRecord(ev, ctx->stream));
-      chunk_done.push_back(ev);
+      VCK(cudaEventRecord(chunk_events.add(), ctx->stream));
     }
     }  // chunks
   }
@@ -1154,7 +1153,6 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
                           ctx->copy_stream));
     }
     VCK(cudaStreamSynchronize(ctx->copy_stream));
-    for (cudaEvent_t ev : chunk_done) cudaEventDestroy(ev);
   }
   // the Scratch buffers are returned to the pool on scope exit; the pool is
   // stream-ordered, so the kernels above keep exclusive use until they finish.

@@ -277,7 +277,7 @@ class SlabBlobs:
         self.plan = make_plan(self.nz, world, rank, hw, 0)
         self.slab_src = None
 
-    def run(self, own_src, minima_threshold=np.inf, maxima_threshold=-np.inf, use_threshold_ratios=True,
+    def run(self, own_src, minima_threshold=np.inf, maxima_threshold=-np.inf, use_threshold_ratios=False,
             capacity=1 << 20):
         import torch
         plan, be = self.plan, self.backend
