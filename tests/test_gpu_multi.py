@@ -9,6 +9,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
+def test_multi_device_c_entry_equals_one_gpu():
+    """visfd_cuda_membrane_multi (one C call, one worker thread per device; tests/cpp/multi_check.cpp) == the one-GPU
+    result bit for bit for 1, 2, 3, 4 and 8 workers -- on as many devices as the box has (a one-GPU box lists the same
+    device several times, which runs the same slab logic)."""
+    exe = os.path.join(ROOT, "tests", "cpp", "multi_check")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "OK (0 failures)" in r.stdout
+
+
+@pytest.mark.gpu
 def test_slab_pipeline_over_nccl_equals_one_gpu():
     import torch
     n = torch.cuda.device_count()

@@ -7,7 +7,7 @@
 namespace visfd_cuda {
 
 static thread_local std::string g_last_error;
-void set_last_error(const std::string &m) { g_last_error = m; }
+void set_last_error(const std::string &m) { g_last_error = m; }   // g_last_error is thread_local
 const char *get_last_error() { return g_last_error.c_str(); }
 
 bool is_device_pointer(const void *p) {
@@ -117,6 +117,12 @@ extern "C" {
 int visfd_cuda_version(void) { return 1; }
 
 const char *visfd_cuda_last_error(void) { return visfd_cuda::get_last_error(); }
+
+int visfd_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
 
 int visfd_cuda_init(int device, visfd_ctx **out) {
   try {
