@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--shape", default=None, help="nz,ny,nx override (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-side-tables", action="store_true", help="skip masked / C5 / multi-GPU C3 / C-entry rows")
     ap.add_argument("--no-cpu-big", action="store_true", help="reference arm: skip the extra 256^3 pass")
     return ap.parse_args()
 
@@ -330,6 +331,188 @@ def blob_c3_row(ctx, dev, hbm_peak):
             "thresholds": "minima < 0, absolute (the -blob-s minima defaults)"}
 
 
+
+def masked_row(ctx, dev):
+    """`-mask` is how membrane detection is normally run (the cell, not the whole tomogram): C4 parameters on a
+    1024 x 1024 x 512 volume with a centred box mask covering 80 % of it.  Masks route the Gaussian through the masked
+    sweeps (denominator volume, no TMA) and add the mask reads to every stage.  Device resident, 1 warm-up + 2 timed."""
+    import torch
+    import visfd_b200
+    from visfd_b200 import synth
+    shape = (512, 1024, 1024)
+    vol = synth.tomogram_torch(shape, dev, seed=4)
+    mask = torch.zeros(shape, dtype=torch.float32, device=dev)
+    f = (1 - 0.8 ** (1 / 3)) / 2
+    lo = [int(round(s * f)) for s in shape]
+    mask[lo[0]:shape[0] - lo[0], lo[1]:shape[1] - lo[1], lo[2]:shape[2] - lo[2]] = 1.0
+    out = torch.empty_like(vol)
+
+    def call():
+        ctx.reset_stage_ms()
+        ctx.membrane(vol, SIGMA, RATIO, visfd_b200.DECREASING_EIVALS, TV_BEST, True, TV_SIGMA, 4, SQ2, mask=mask, out=out)
+
+    call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(2):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    n = float(np.prod(shape))
+    stage = {k: ctx.stage_ms(k) for k in ("gauss", "ridge", "select", "compact", "tv")}
+    row = {"shape_zyx": list(shape), "mask": "centred box, 80 % of the volume", "ms": ms,
+           "Gvoxel_per_s": n / ms / 1e6, "masked_fraction": float(1.0 - mask.mean().item()),
+           "voters": int(ctx.last_voter_count()), "stage_ms": stage, "tv_kernel": ctx.last_tv_kernel()}
+    del vol, mask, out
+    torch.cuda.empty_cache()
+    return row
+
+
+def c5_row(ctx, dev, dist, rank, world):
+    """BASELINE config 5: 4096 x 4096 x 1024, the full filter_mrc membrane pipeline (blur, eigensolve, voting) and the
+    final `-thresh` at the 99th percentile of the post-vote saliency (a second filter_mrc invocation in the
+    reference), sharded as Z-slabs over all ranks.  The percentile is a distributed radix select
+    over the result (the same all-reduced histograms as the cut), the threshold map is visfd_cuda_threshold.
+    1 warm-up + 2 timed steps, CUDA events, max over ranks."""
+    import torch
+    import visfd_b200
+    from visfd_b200 import synth, MembraneParams
+    from visfd_b200.slab import SlabMembrane, distributed_cut_threshold
+    shape = WORKLOADS["C5"]
+    nz, ny, nx = shape
+    params = MembraneParams(SIGMA, RATIO, visfd_b200.DECREASING_EIVALS, TV_BEST, 1, TV_SIGMA, 4, SQ2)
+    pipe = SlabMembrane(ctx, shape, params, rank=rank, world=world, dist=dist if world > 1 else None, device=dev)
+    z0, z1 = pipe.plan.own
+    own = synth.tomogram_torch(shape, dev, seed=0, z0=z0, z1=z1)
+    out = torch.empty_like(own)
+    maskmap = torch.empty_like(own)
+    state = {}
+
+    def step():
+        pipe.run(own, out=out)
+        # k = floor(n * 0.01)-th largest value = the 99th percentile
+        T = distributed_cut_threshold(ctx, out, 0.01, dist=dist, world=world, device=dev)
+        ctx.threshold(out, visfd_b200.THRESH_SINGLE, [T], out=maskmap)
+        state["T"] = T
+
+    step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(2):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 2], device=dev, dtype=torch.float64)
+    ones = maskmap.sum(dtype=torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ones)
+    n = float(nz) * ny * nx
+    row = {"shape_zyx": list(shape), "ms_per_step": float(t.item()), "Gvoxel_per_s": n / float(t.item()) / 1e6,
+           "threshold_99th_percentile": float(state["T"]), "voxels_above": int(ones.item()),
+           "fraction_above": float(ones.item()) / n, "stages": "gauss + ridge + cut + voting + score + percentile + thresh"}
+    del pipe, own, out, maskmap
+    torch.cuda.empty_cache()
+    ctx.trim()
+    return row
+
+
+def blob_c3_multi_row(ctx, dev, dist, rank, world):
+    """BASELINE config 3 over Z-slabs (visfd_b200.slab.SlabBlobs): 12 LoG scales + 10 extremum scans on
+    1024 x 1024 x 512, halo = widest LoG half-width + 1 planes, candidate lists all-gathered, best scores all-reduced."""
+    import torch
+    from visfd_b200 import synth
+    from visfd_b200.slab import SlabBlobs
+    shape = WORKLOADS["C3"]
+    n_scales = 12
+    sigmas = 2.0 * 4.0 ** (np.arange(n_scales) / n_scales)
+    ratio = float(np.sqrt(-2.0 * np.log(0.03)))
+    blobs = SlabBlobs(ctx, shape, sigmas, delta=0.02, truncate_ratio=ratio, rank=rank, world=world,
+                      dist=dist if world > 1 else None, device=dev)
+    z0, z1 = blobs.plan.own
+    own = synth.tomogram_torch(shape, dev, seed=2, z0=z0, z1=z1, n_shells=0)
+
+    def call():
+        return blobs.run(own, minima_threshold=0.0, maxima_threshold=-np.inf, use_threshold_ratios=False,
+                         capacity=1 << 24)
+
+    mn, mx = call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(2):
+        call()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 2], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n = float(np.prod(shape))
+    row = {"shape_zyx": list(shape), "scales": n_scales, "ms": float(t.item()),
+           "Gvoxel_scales_per_s": n * n_scales / float(t.item()) / 1e6, "minima": int(len(mn)), "maxima": int(len(mx)),
+           "halo_planes": blobs.plan.halo, "note": "noise volume without stamped blobs (the lists are all-gathered "
+           "through the host: their size is part of the cost)"}
+    del own, blobs
+    torch.cuda.empty_cache()
+    return row
+
+
+def c_multi_row(dev, dist, rank, world, shape, want_checksum):
+    """The same workload through visfd_cuda_membrane_multi: ONE process (rank 0) drives all `world` GPUs of the node
+    from pinned host arrays through the C entry a C++ filter_mrc would link; the other ranks have released their
+    memory and wait at the barrier.  Upload and download are inside the timed region (it is an end-to-end figure).
+    1 warm-up + 1 timed call, wall clock around the call and max of the workers' device times."""
+    import torch
+    import visfd_b200
+    from visfd_b200 import synth
+    row = None
+    if rank == 0:
+        nz, ny, nx = shape
+        h_src = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        h_out = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        step = 64
+        for z in range(0, nz, step):
+            h_src[z:z + step].copy_(synth.tomogram_torch(shape, dev, seed=0, z0=z, z1=min(nz, z + step)))
+        torch.cuda.empty_cache()
+        src_np, out_np = h_src.numpy(), h_out.numpy()
+        devices = list(range(world))
+        res = None
+        times = []
+        for it in range(2):
+            t = time.perf_counter()
+            res = visfd_b200.membrane_multi(devices, src_np, SIGMA, RATIO, visfd_b200.DECREASING_EIVALS, TV_BEST, True,
+                                            TV_SIGMA, 4, SQ2, out=out_np)
+            times.append(time.perf_counter() - t)
+        n = float(nz) * ny * nx
+        bits = int(h_out.view(torch.int32).sum(dtype=torch.int64).item())
+        row = {"call": "visfd_cuda_membrane_multi(ndev=%d, host arrays)" % world, "wall_ms": times[-1] * 1e3,
+               "device_ms_max": max(res["device_ms"]), "device_ms": res["device_ms"],
+               "Gvoxel_per_s": n / times[-1] / 1e9, "h2d_bytes": int(4 * n), "d2h_bytes": int(4 * n),
+               "bits_sum_i64": bits, "matches_checksum": bool(bits == want_checksum)}
+        del h_src, h_out
+    if world > 1:
+        # the other ranks wait on the HOST (a key in the rendezvous store), not in an NCCL barrier: a collective
+        # kernel spinning on a GPU that rank 0 is driving from another process would have to be time-sliced against it
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("visfd_c_multi_done", "1")
+        else:
+            store.wait(["visfd_c_multi_done"], datetime.timedelta(minutes=30))
+    return row
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -362,6 +545,7 @@ def main():
         raise SystemExit("bench.py: workload %s needs ~%.0f GB of HBM per GPU at N=%d, %.0f GB free" %
                          (name, need / 1e9, world, free_b / 1e9))
 
+    own = out = d_out = h_src = h_out = src_np = out_np = None
     ctx = visfd_b200.Context(local, stream=torch.cuda.current_stream().cuda_stream)
     params = MembraneParams(SIGMA, RATIO, visfd_b200.DECREASING_EIVALS, TV_BEST, 1, TV_SIGMA, 4, SQ2)
     pipe = SlabMembrane(ctx, shape, params, rank=rank, world=world, dist=dist if world > 1 else None, device=dev)
@@ -509,6 +693,26 @@ def main():
                "call": "visfd_cuda_membrane(host pointers)" if world == 1 else
                        "pinned host slab -> H2D -> SlabMembrane.run(out_host=pinned) -> chunked D2H, per rank"}
 
+    # ---- side tables: masked run (N = 1); C5 + multi-GPU C3 + the one-call C entry (N > 1) ---------------
+    masked = c5 = blob_multi = c_multi = None
+    if not args.no_side_tables:
+        own = out = d_out = h_src = h_out = src_np = out_np = e2e_step = device_step = None   # release the C4 buffers
+        pipe.smoothed = pipe.saliency = pipe.slab_src = None
+        torch.cuda.empty_cache()
+        ctx.trim()
+        if world == 1:
+            masked = masked_row(ctx, dev)
+        else:
+            blob_multi = blob_c3_multi_row(ctx, dev, dist, rank, world)
+            if world == 8:
+                c5 = c5_row(ctx, dev, dist, rank, world)
+            ctx.trim()
+            torch.cuda.empty_cache()
+            torch.cuda.synchronize()
+            dist.barrier()          # everybody has released its memory and is idle
+            torch.cuda.synchronize()
+            c_multi = c_multi_row(dev, dist, rank, world, shape, checksum["bits_sum_i64"])
+
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -523,6 +727,7 @@ def main():
                 "config": workload_config(name, shape), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "checksum": checksum,
                 "roofline": roofline, "roofline_gauss": gauss, "roofline_ridge": ridge, "gauss_c2": gauss_c2, "blob_c3": blob_c3,
+                "masked_1024": masked, "c5_n8": c5, "blob_c3_multi": blob_multi, "c_entry_multi": c_multi,
                 "cpu_baseline": cpu,
                 "stage_ms_rank0_last_step": stage, "halo_planes": pipe.plan.halo if world > 1 else 0}
         print(json.dumps(line), file=RESULT_OUT, flush=True)

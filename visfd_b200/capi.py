@@ -177,6 +177,28 @@ def tv_halfwidth(sigma, cutoff_ratio):
     return load_library().visfd_cuda_tv_halfwidth(_f(sigma), _f(cutoff_ratio))
 
 
+def membrane_multi(devices, src, sigma, truncate_ratio, order, cut, cut_is_fraction, tv_sigma, tv_exponent,
+                   tv_cutoff_ratio, mask=None, out=None, lib=None):
+    """visfd_cuda_membrane_multi: the fused pipeline of HandleTV on several GPUs of this node behind one C call
+    (one worker thread per device, Z-slabs, host arrays in and out).  devices: list of CUDA device indices (a device
+    may appear more than once).  -> dict(out, threshold, device_ms).  numpy (host) arrays only."""
+    lib = lib or load_library()
+    src = np.ascontiguousarray(src, np.float32)
+    mask = None if mask is None else np.ascontiguousarray(mask, np.float32)
+    res = out if out is not None else np.empty(src.shape, np.float32)
+    assert isinstance(res, np.ndarray) and res.dtype == np.float32 and res.flags.c_contiguous and res.shape == src.shape
+    p = MembraneParams(sigma, truncate_ratio, order, cut, int(cut_is_fraction), tv_sigma, tv_exponent, tv_cutoff_ratio)
+    devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+    ms = (C.c_double * len(devices))()
+    thr = _f()
+    nz, ny, nx = src.shape
+    rc = lib.visfd_cuda_membrane_multi(_i(len(devices)), devs, _i64(nx), _i64(ny), _i64(nz), _ptr(src), _ptr(mask),
+                                       C.byref(p), _ptr(res), C.byref(thr), ms)
+    if rc != 0:
+        raise VisfdCudaError(lib.visfd_cuda_last_error().decode())
+    return dict(out=res, threshold=thr.value, device_ms=list(ms))
+
+
 class Context:
     """One context per GPU (visfd_cuda_init)."""
 
