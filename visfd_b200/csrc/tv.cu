@@ -268,10 +268,24 @@ struct __align__(16) VoterRec {
   float4 a;  // {-x, -y, -z, log2(4w)/2}
   float4 b;  // {nx, ny, nz, log2(4w)}
   float4 c;  // {nx/2, ny/2, nz/2, 4w}       w = saliency * mask weight / table total
-  // table kernel (lut): a = {-x, -y, -z, L^2}, b = {L nx, L ny, L nz, L}, c = {L nx/2, L ny/2, L nz/2, 0}
-  // with L = (4w)^(1/6): the vote u = sqrt(4w decay) cos^2 (n/2 - q r) picks up L from the dot
-  // product, L^2 from cos^2 and L from n/2, so the weight costs no instruction in the loop
+  // table kernel (lut), L = (4w)^(1/6): the vote u = sqrt(4w decay) cos^2 (n/2 - q r) picks up L from the dot
+  // product, L^2 from cos^2 and L from n/2, so the weight costs no instruction in the loop.  The fields carry
+  // power-of-two scales (exact; see LUT_* below) chosen so that the r^2 accumulator of the loop is a DENORMAL
+  // float whose bit pattern is the shared-memory address of the table row:
+  //   a = {-x rho, -y rho, -z rho, L^2 K}, b = {L n beta, L}, c = {L n beta2, 0}
 };
+// rho^2 = 2^-142 = LUT_ROW ulps of the denormal range: (rho r)^2 accumulates to bits = base + 128 r^2.
+// With ninv' = -tau / r^2 from the table: d' = (rho r).(beta L n) = rho beta L d, qn' = d' ninv' = -(rho beta tau) L q,
+// ang' = qn' d' + K L^2 = K L^2 cos^2 (K = rho^2 beta^2 tau), h' = qn' (rho r) + beta2 L n = 2 beta2 L (n/2 - q r)
+// (beta2 = rho^2 beta tau / 2), and the table's E' = E / (2 beta2 K) restores the scale.  Every intermediate is a
+// normal float of moderate exponent; all scalings are powers of two, so the results are those of the unscaled form.
+constexpr int LUT_RHO_LOG2 = -71, LUT_BETA_LOG2 = 40, LUT_TAU_LOG2 = 100;
+constexpr int LUT_K_LOG2 = 2 * LUT_RHO_LOG2 + 2 * LUT_BETA_LOG2 + LUT_TAU_LOG2;        // 38
+constexpr int LUT_BETA2_LOG2 = 2 * LUT_RHO_LOG2 + LUT_BETA_LOG2 + LUT_TAU_LOG2 - 1;    // -3
+constexpr int LUT_E_LOG2 = -(1 + LUT_BETA2_LOG2 + LUT_K_LOG2);                         // -36
+__host__ __device__ __forceinline__ float pow2f(int e) {   // 2^e, -126 <= e <= 127
+  union { unsigned u; float f; } v; v.u = (unsigned)(e + 127) << 23; return v.f;
+}
 
 struct DirSrc {
   const float *direction;  // N*3, or NULL
@@ -366,7 +380,8 @@ voter_fill_kernel(VoterSrc v, i64 n_regions, const uint32_t *__restrict__ off, f
       const float px = -(float)(bp.bx * BR + tx), py = -(float)(bp.by * BR + ty), pz = -(float)(bp.bz * BR + tz);
       if (lut) {   // only used when every weight is positive (checked by the host before the launch)
         const float lam = (float)pow((double)fmaxf(w4, 0.0f), 1.0 / 6.0);
-        r->a = make_float4(px, py, pz, lam * lam);
+        const float rho = pow2f(LUT_RHO_LOG2);
+        r->a = make_float4(px * rho, py * rho, pz * rho, lam * lam * pow2f(LUT_K_LOG2));
         r->b.w = lam;
         r->c.w = 0.0f;
       } else {
@@ -386,15 +401,17 @@ voter_direction_kernel(DirSrc d, int nx, int ny, uint32_t n_voters, bool lut, Vo
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= n_voters) return;
   VoterRec *r = rec + i;
-  const float4 a = r->a;
+  float4 a = r->a;
+  if (lut) { const float un = pow2f(-LUT_RHO_LOG2); a.x *= un; a.y *= un; a.z *= un; }
   float n[3];
   voter_direction(d, nx, ny, (int)(-a.x), (int)(-a.y), (i64)(-a.z), n);
+  float sb = 1.0f, sc = 0.5f;
   if (lut) {
     const float lam = r->b.w;
-    n[0] *= lam; n[1] *= lam; n[2] *= lam;
+    sb = lam * pow2f(LUT_BETA_LOG2); sc = lam * pow2f(LUT_BETA2_LOG2);
   }
-  r->b.x = n[0]; r->b.y = n[1]; r->b.z = n[2];
-  r->c.x = 0.5f * n[0]; r->c.y = 0.5f * n[1]; r->c.z = 0.5f * n[2];
+  r->b.x = sb * n[0]; r->b.y = sb * n[1]; r->b.z = sb * n[2];
+  r->c.x = sc * n[0]; r->c.y = sc * n[1]; r->c.z = sc * n[2];
 }
 
 // ---------------------------------------------------------------------------------
@@ -569,18 +586,28 @@ __device__ __forceinline__ void vote(const VoterRec *q, float fx, float fy, floa
 
 
 // ---- table variant (exponent 4, weights > 0) ---------------------------------------------------
-// r2 is an integer < 2^16, so LUT_MAGIC + r2 is exact and its bit pattern is bits(LUT_MAGIC) + 128 r2:
-// a byte offset into a table of 128-byte rows (16 replicas of {E, -1/r2}; a lane reads replica lane & 15,
-// so the 16 lanes of a half-warp -- which share the voter -- cover all 32 banks exactly once).
-constexpr float LUT_MAGIC = 65536.0f;   // ulp 2^-7
+// The table holds 128-byte rows, one per integer r^2: 16 replicas of {E', -tau/r^2}; a lane reads replica
+// lane & 15, so the 16 lanes of a half-warp -- which share the voter -- cover all 32 banks exactly once.
+// The r^2 accumulator starts at the bit pattern of the lane's replica address (a denormal float, the shared
+// window is < 2^23 bytes) and every (rho r)^2 term adds 128 ulps per unit of r^2 exactly (denormal arithmetic is
+// fixed point), so its bits ARE the address of the row: no conversion, no add.  (Round 1 of this kernel used
+// MAGIC = 65536 + r^2 and an IADD3 per lookup; together with the MOVs that re-paired the two lookups for a
+// packed multiply that was 10 of ~106 issue slots per voter and lane.)
 constexpr int LUT_ROW = 128;            // bytes per r2
 constexpr int LUT_MAX_HW = 24;
 struct LutState {
-  unsigned tab;      // shared-window address of the lane's replica, minus bits(LUT_MAGIC)
-  float r2m_max;     // LUT_MAGIC + (n_lut - 1)
+  float base;        // bit pattern = shared-window address of the lane's replica of row 0
+  float r2m_max;     // bit pattern = address of the lane's replica of the last row (CLAMP)
 };
-__device__ __forceinline__ float2 lut_fetch(float r2m, unsigned tab) {
-  return *reinterpret_cast<const float2 *>(__cvta_shared_to_generic(__float_as_uint(r2m) + tab));
+__device__ __forceinline__ float2 lut_fetch(float r2m) {
+  float2 t;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(__float_as_uint(r2m)));
+  return t;
+}
+__device__ __forceinline__ float fmul_s(float a, float b) {   // a scalar multiply ptxas may not re-pair
+  float d;
+  asm("mul.rn.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
 }
 template <bool CURVES, bool CLAMP>
 __device__ __forceinline__ void vote_pair_lut(float rx, float ry, float rxy2m, float dxy, float2 fz, const float4 &ea,
@@ -588,15 +615,17 @@ __device__ __forceinline__ void vote_pair_lut(float rx, float ry, float rxy2m, f
   const float2 rz = __fadd2_rn(fz, bc(ea.z));
   float2 r2m = __ffma2_rn(rz, rz, bc(rxy2m));
   if (CLAMP) { r2m.x = fminf(r2m.x, L.r2m_max); r2m.y = fminf(r2m.y, L.r2m_max); }
-  const float2 d = __ffma2_rn(rz, bc(eb.z), bc(dxy));        // L (r.n)
-  const float2 t0 = lut_fetch(r2m.x, L.tab), t1 = lut_fetch(r2m.y, L.tab);
-  const float2 ee = make_float2(t0.x, t1.x), ninv = make_float2(t0.y, t1.y);
-  const float2 qn = __fmul2_rn(d, ninv);                     // -L q
-  float2 ang2;                                               // L^2 cos^2 (surfaces) / -L^2 sin^2 (curves)
+  const float2 d = __ffma2_rn(rz, bc(eb.z), bc(dxy));        // d'
+  const float2 t0 = lut_fetch(r2m.x), t1 = lut_fetch(r2m.y);
+  // {E', ninv'} of the two receivers arrive as two register pairs; multiplying them in scalar form costs the
+  // same two FMA-pipe cycles as one packed multiply and saves the two MOVs that would re-pair them
+  float2 qn, w;
+  qn.x = fmul_s(d.x, t0.y); qn.y = fmul_s(d.y, t1.y);        // qn'
+  float2 ang2;                                               // K L^2 cos^2 (surfaces) / -K L^2 sin^2 (curves)
   if (CURVES) ang2 = __fmul2_rn(qn, d);
   else ang2 = __ffma2_rn(qn, d, bc(ea.w));
-  const float2 w = __fmul2_rn(ee, ang2);                     // sign irrelevant: squared below
-  const float2 hx = __ffma2_rn(qn, bc(rx), bc(ec.x));        // L (n/2 - q r)
+  w.x = fmul_s(t0.x, ang2.x); w.y = fmul_s(t1.x, ang2.y);    // sign irrelevant: squared below
+  const float2 hx = __ffma2_rn(qn, bc(rx), bc(ec.x));        // h'
   const float2 hy = __ffma2_rn(qn, bc(ry), bc(ec.y));
   const float2 hz = __ffma2_rn(qn, rz, bc(ec.z));
   const float2 wx = __fmul2_rn(w, hx), wy = __fmul2_rn(w, hy), wz = __fmul2_rn(w, hz);
@@ -611,8 +640,8 @@ template <bool CURVES, bool CLAMP>
 __device__ __forceinline__ void vote_lut(const VoterRec *q, float fx, float fy, float2 fz01, float2 fz23, const LutState &L,
                                          float2 T[12]) {
   const float4 ea = q->a, eb = q->b, ec = q->c;
-  const float rx = fx + ea.x, ry = fy + ea.y;
-  const float rxy2m = fmaf(ry, ry, fmaf(rx, rx, LUT_MAGIC));
+  const float rx = fx + ea.x, ry = fy + ea.y;                // rho r
+  const float rxy2m = fmaf(ry, ry, fmaf(rx, rx, L.base));
   const float dxy = fmaf(ry, eb.y, rx * eb.x);
   vote_pair_lut<CURVES, CLAMP>(rx, ry, rxy2m, dxy, fz01, ea, eb, ec, L, T);
   vote_pair_lut<CURVES, CLAMP>(rx, ry, rxy2m, dxy, fz23, ea, eb, ec, L, T + 6);
@@ -713,11 +742,14 @@ __device__ __forceinline__ void gather_patch(const GatherArgs &g, const unsigned
 
   // ---- receivers of this lane: (ix, iy, pz .. pz+3); its voters: every second ring entry ----
   const int ix = px + (lane & 3), iy = py + ((lane >> 2) & 3), half = lane >> 4;
-  const float fx = (float)ix, fy = (float)iy;
-  const float2 fz01 = make_float2((float)pz, (float)(pz + 1)), fz23 = make_float2((float)(pz + 2), (float)(pz + 3));
-  const float pcx = px + 1.5f, pcy = py + 1.5f, pcz = pz + 1.5f;
+  // (the table kernel works in coordinates scaled by rho = 2^-71, see LUT_*: every comparison below is exact in
+  // either scale, the squared distances of the scaled form being fixed-point denormals)
+  const float cs = LUT ? pow2f(LUT_RHO_LOG2) : 1.0f;
+  const float fx = (float)ix * cs, fy = (float)iy * cs;
+  const float2 fz01 = make_float2((float)pz * cs, (float)(pz + 1) * cs), fz23 = make_float2((float)(pz + 2) * cs, (float)(pz + 3) * cs);
+  const float pcx = (px + 1.5f) * cs, pcy = (py + 1.5f) * cs, pcz = (pz + 1.5f) * cs, box = 1.5f * cs;
   const float negc = g.neg_c;  // already halved on the host for the SQRTW kernels
-  const float lim_in = g.lim_in, lim_pass = g.lim_pass;
+  const float lim_in = g.lim_in, lim_pass = (g.lim_pass * cs) * cs;
   float2 T[12];
 #pragma unroll
   for (int k = 0; k < 12; k++) T[k] = make_float2(0.0f, 0.0f);
@@ -730,9 +762,9 @@ __device__ __forceinline__ void gather_patch(const GatherArgs &g, const unsigned
   };
   auto reach = [&](const float4 &a) -> bool {
     // exact distance from the voter (a holds the NEGATED position) to the patch box
-    const float gx = fmaxf(fabsf(a.x + pcx) - 1.5f, 0.0f);
-    const float gy = fmaxf(fabsf(a.y + pcy) - 1.5f, 0.0f);
-    const float gz = fmaxf(fabsf(a.z + pcz) - 1.5f, 0.0f);
+    const float gx = fmaxf(fabsf(a.x + pcx) - box, 0.0f);
+    const float gy = fmaxf(fabsf(a.y + pcy) - box, 0.0f);
+    const float gz = fmaxf(fabsf(a.z + pcz) - box, 0.0f);
     return fmaf(gx, gx, fmaf(gy, gy, gz * gz)) < lim_pass;
   };
   auto enqueue = [&](int slot, uint32_t gi) {
@@ -789,7 +821,7 @@ __device__ __forceinline__ void gather_patch(const GatherArgs &g, const unsigned
     if (slot >= TV_QCAP) slot -= TV_QCAP;
     if (LUT) {
       // a zero vote: the lane's own position (r = 0, so the index stays inside the table) and L = 0
-      ring[slot].a = make_float4(-(float)px, -(float)py, -(float)pz, 0.0f);
+      ring[slot].a = make_float4(-(float)px * cs, -(float)py * cs, -(float)pz * cs, 0.0f);
       ring[slot].b = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       const float ninf = __int_as_float(0xff800000u);  // ex2(-inf) = 0
@@ -857,7 +889,7 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
   const unsigned slot = blockIdx.x * TV_WARPS + (threadIdx.x >> 5);   // warp slot: 4 per tile
   const size_t per_warp = TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t);
   unsigned char *mine = tv_smem + (threadIdx.x >> 5) * ((per_warp + 15) & ~(size_t)15);
-  LutState L{0u, 0.0f};
+  LutState L{0.0f, 0.0f};
   gather_patch<EXPO, CURVES, POSW, SHELL, 0>(g, slot, mine, L);
 }
 
@@ -885,8 +917,9 @@ __global__ void __launch_bounds__(32 * LUT_WARPS, 1) tv_gather_lut_kernel(Gather
   const size_t per_warp = (TV_QCAP * sizeof(VoterRec) + (2 * (size_t)g.row_cap + 4) * sizeof(uint32_t) + 15) & ~(size_t)15;
   unsigned char *mine = tv_smem + tab_bytes + w * per_warp;
   LutState L;
-  L.tab = (unsigned)__cvta_generic_to_shared(tv_smem) + 8u * (lane & 15) - __float_as_uint(LUT_MAGIC);
-  L.r2m_max = LUT_MAGIC + (float)(g.n_lut - 1);
+  const unsigned replica = (unsigned)__cvta_generic_to_shared(tv_smem) + 8u * (lane & 15);
+  L.base = __uint_as_float(replica);
+  L.r2m_max = __uint_as_float(replica + (unsigned)LUT_ROW * (unsigned)(g.n_lut - 1));
   for (;;) {
     unsigned t = 0, tile = 0;
     if (lane == 0) {
@@ -1053,7 +1086,8 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
       std::vector<float2> h(g.n_lut);
       for (int r2 = 0; r2 < g.n_lut; r2++) {
         const float e = ((float)r2 < g.lim_in) ? (float)exp(-0.5 * (double)r2 / ((double)p.sigma * (double)p.sigma)) : 0.0f;
-        h[r2] = make_float2(e, r2 ? (float)(-1.0 / (double)r2) : 0.0f);
+        // {E', ninv'} in the scales of the table kernel's records (LUT_*); powers of two: exact
+        h[r2] = make_float2(ldexpf(e, LUT_E_LOG2), r2 ? ldexpf((float)(-1.0 / (double)r2), LUT_TAU_LOG2) : 0.0f);
       }
       if (lut_mode == 2) h[g.n_lut - 1] = make_float2(0.0f, 0.0f);
       lut.reset(ctx, h.size());
