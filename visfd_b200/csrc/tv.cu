@@ -482,6 +482,11 @@ __device__ __forceinline__ int axis_gap(int lo_a, int hi_a, int lo_b, int hi_b) 
 }
 
 constexpr int TV_DRAIN = 32;             // voters evaluated per drain
+constexpr int TV_GROUP = 8;              // voters per unrolled iteration of a drain (4 per half-warp) ...
+#ifndef TV_GROUP_LUT_N
+#define TV_GROUP_LUT_N 16
+#endif
+constexpr int TV_GROUP_LUT = TV_GROUP_LUT_N;   // ... and in the table kernel (8 per half-warp: -2.7 % in isolation)
 // ring capacity: at most TV_DRAIN - 1 + 64 voters are queued when a streaming iteration (64 candidates,
 // two per lane; three per lane measured no faster) starts, and it adds up to 64 more before the whole
 // batches among the former are drained
@@ -654,10 +659,11 @@ template <int EXPO, bool CURVES, bool POSW, bool SHELL, int LUT>
 __device__ __forceinline__ void drain(const VoterRec *q, int n, float fx, float fy, float2 fz01, float2 fz23,
                                       const GatherArgs &g, float negc, float lim_in, const LutState &L, float2 T[12]) {
   const VoterRec *end = q + n;
+  constexpr int G = LUT ? TV_GROUP_LUT : TV_GROUP;
 #pragma unroll 1
-  for (; q < end; q += 8) {
+  for (; q < end; q += G) {
 #pragma unroll
-    for (int u = 0; u < 8; u += 2) {
+    for (int u = 0; u < G; u += 2) {
       if (LUT) vote_lut<CURVES, LUT == 2>(q + u, fx, fy, fz01, fz23, L, T);
       else vote<EXPO, CURVES, POSW, SHELL>(q + u, fx, fy, fz01, fz23, g, negc, lim_in, T);
     }
@@ -816,7 +822,8 @@ __device__ __forceinline__ void gather_patch(const GatherArgs &g, const unsigned
   }
   // leftovers (< 160), padded to a multiple of 4 with zero-weight voters
   cp_async_wait<0>();
-  if (lane < ((8 - (cnt & 7)) & 7)) {
+  constexpr int G = LUT ? TV_GROUP_LUT : TV_GROUP;   // voters per unrolled drain iteration
+  if (lane < ((G - (cnt & (G - 1))) & (G - 1))) {
     int slot = head + cnt + lane;
     if (slot >= TV_QCAP) slot -= TV_QCAP;
     if (LUT) {
@@ -831,7 +838,7 @@ __device__ __forceinline__ void gather_patch(const GatherArgs &g, const unsigned
     ring[slot].c = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncwarp();
-  cnt = (cnt + 7) & ~7;
+  cnt = (cnt + G - 1) & ~(G - 1);
   while (cnt > 0) {
     const int n = min(cnt, min(TV_DRAIN, TV_QCAP - head));
     drain<EXPO, CURVES, POSW, SHELL, LUT>(ring + head + half, n, fx, fy, fz01, fz23, g, negc, lim_in, L, T);
