@@ -186,6 +186,53 @@ def test_tensor_score_matches_reference_eigen(ctx, oracle, golden):
     assert rel_err(sc, golden["tv_score_planar"]) <= 1e-5
 
 
+def test_newton_eigenvalues_match_closed_form(ctx):
+    """sym3_eigenvalues_newton (eigen3.cuh: Newton step on the characteristic polynomial, no transcendental
+    functions) against LAPACK in float64 on float32 matrices: generic, nearly double and triple eigenvalues at
+    either end of the spectrum, rank one, diagonal, identity multiples, zero, and scales from 1e-12 to 1e12."""
+    rng = np.random.default_rng(5)
+    mats = []
+
+    def from_spectrum(lam, n):
+        q, _ = np.linalg.qr(rng.standard_normal((n, 3, 3)))
+        return np.einsum("nij,nj,nkj->nik", q, np.broadcast_to(lam, (n, 3)) if np.ndim(lam) == 1 else lam, q)
+
+    n = 20000
+    mats.append(from_spectrum(rng.standard_normal((n, 3)), n))
+    for eps in (1e-1, 1e-3, 1e-5, 1e-7, 0.0):
+        lam = rng.standard_normal((n // 4, 3))
+        lam[:, 1] = lam[:, 0] * (1 + eps * rng.standard_normal(n // 4))          # a nearly double pair
+        mats.append(from_spectrum(lam, n // 4))
+        lam = 1 + eps * rng.standard_normal((n // 4, 3))                           # nearly triple
+        mats.append(from_spectrum(lam, n // 4) * rng.choice([-1.0, 1.0], (n // 4, 1, 1)))
+    v = rng.standard_normal((n // 4, 3))
+    mats.append(np.einsum("ni,nj->nij", v, v))                                     # rank one (membrane-like)
+    d = np.zeros((n // 4, 3, 3))
+    d[:, [0, 1, 2], [0, 1, 2]] = rng.standard_normal((n // 4, 3))
+    mats.append(d)
+    mats.append(np.eye(3)[None] * rng.standard_normal((64, 1, 1)))
+    mats.append(np.zeros((8, 3, 3)))
+    a = np.concatenate(mats)
+    a = a * 10.0 ** rng.integers(-12, 13, (len(a), 1, 1))
+    a = 0.5 * (a + np.swapaxes(a, 1, 2))
+    flat = np.stack([a[:, 0, 0], a[:, 1, 1], a[:, 2, 2], a[:, 0, 1], a[:, 1, 2], a[:, 0, 2]], -1).astype(np.float32)
+    a64 = np.zeros((len(flat), 3, 3))
+    for k, (i, j) in enumerate([(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)]):
+        a64[:, i, j] = a64[:, j, i] = flat[:, k].astype(np.float64)
+    want = np.linalg.eigvalsh(a64)                                                 # ascending
+    scale = np.abs(want).max(axis=1, keepdims=True) + 1e-300
+    for order in (0, 1):
+        _, ev, _ = ctx.tensor_score(flat.reshape(-1, 1, 1, 6), order=order, score_kind=vb.SCORE_PLANAR,
+                                    is_vote_tensor=False, want_eivals=True)
+        ev = ev.reshape(-1, 3).astype(np.float64)
+        w = want.copy()
+        if order == 1:        # decreasing = first and last exchanged (eigen3_simple.hpp:252-264)
+            w[:, [0, 2]] = w[:, [2, 0]]
+        err = np.abs(ev - w) / scale
+        # float32 output: half an ulp of the scale, plus the ~1e-8 of a nearly double root (as the reference)
+        assert err.max() <= 1.0e-7, (order, err.max(), flat[np.argmax(err.max(axis=1))])
+
+
 @pytest.mark.parametrize("order", [0, 1])
 def test_hessian_ridge(ctx, oracle, order):
     vol = synth.tomogram((36, 44, 52), seed=10)

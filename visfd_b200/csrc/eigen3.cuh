@@ -99,13 +99,85 @@ __device__ __forceinline__ void normalize3d(double a[3]) {  // lin3_utils.hpp:14
   }
 }
 
+// ---- eigenvalues without transcendental functions ------------------------------------------------
+// The closed form above spends ~500 instructions per matrix in double-precision atan2 / sincos / sqrt /
+// division sequences.  The same numbers (to ~1e-12 of the matrix scale) come from the characteristic
+// polynomial itself: with s = m - (trace/3) I, A = -(sum of principal 2x2 minors of s) >= 0 and det = |s|,
+// the shifted eigenvalues are the roots of y^3 - A y - det = 0.  Writing y = 2 rho t (rho^2 = A/3) gives
+// 4 t^3 - 3 t = k, k = det / (2 rho^3) in [-1, 1].  For k >= 0 the LARGEST root is simple and well
+// separated (t in [sqrt(3)/2, 1], derivative >= 6); for k < 0 the same holds for the smallest root, which
+// is the largest root of the problem with det -> -det.  So:
+//   1. t0 = P4(|k|), a degree-4 fit of cos(acos(k)/3) on [0, 1] (max error 4.5e-6), with 1/rho from
+//      MUFU.RSQ64H (rsqrt.approx.f64: no float<->double conversion, which costs as much as four DFMAs here);
+//   2. two Newton steps on y^3 - A y - |det| in double, the reciprocal of the derivative once from
+//      MUFU.RCP64H (error 5e-6 -> ~1e-10 -> rounding level);
+//   3. the other two roots from the deflated quadratic, y = (-z -+ sqrt(4A - 3 z^2)) / 2, its square root
+//      by MUFU.RSQ64H and one Heron step.  (A nearly double root at this end is as ill-conditioned in the
+//      reference's formula -- sqrt(q), q = a^3 - b^2 -- as it is here: ~1e-8 of the scale in double.)
+// ~58 FP64 instructions and 3 MUFU; no division, no branch.  Measured against the closed form: see
+// tests/test_gpu_parity.py::test_newton_eigenvalues_match_closed_form.
+__device__ __forceinline__ double rsqrt_approx64(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+__device__ __forceinline__ double rcp_approx64(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+
+// ev[0] <= ev[1] <= ev[2]
+__device__ __forceinline__ void sym3_eigenvalues_newton(const Sym3d &m, double ev[3]) {
+  const double TINY = 1e-300;   // keeps 1/rho, 1/g' and 1/sqrt(D) finite for multiples of the identity
+  const double shift = (m.xx + m.yy + m.zz) * (1.0 / 3.0);
+  const double sx = m.xx - shift, sy = m.yy - shift, sz = m.zz - shift;
+  const double A = fma(0.5, fma(sz, sz, fma(sy, sy, sx * sx)), fma(m.xz, m.xz, fma(m.yz, m.yz, m.xy * m.xy)));
+  const double det = fma(sx, fma(sy, sz, -m.yz * m.yz),
+                         fma(m.xy, fma(m.yz, m.xz, -m.xy * sz), m.xz * fma(m.xy, m.yz, -sy * m.xz)));
+  const double A3 = fma(A, 1.0 / 3.0, TINY);               // rho^2
+  const double rinv = rsqrt_approx64(A3);                  // 1/rho, 20 bits
+  const double ad = fabs(det);
+  const double k = (ad * (0.5 * rinv)) * (rinv * rinv);    // in [0, 1 + 3e-6]
+  // 2 cos(acos(k)/3), k in [0, 1]
+  const double t2 = fma(fma(fma(fma(-0.008198810912827108, k, 0.03528472977563763), k, -0.09201052271579164), k,
+                            0.33285803676124636), k, 1.7320597067184762);
+  double z = (A3 * rinv) * t2;                             // rho * 2t: within 5e-6 of the largest root
+  // Two Newton steps with the same reciprocal derivative (g' >= 6 rho^2 near the root): 5e-6 -> 1e-10 -> rounding.
+  // The second one matters when the OTHER two roots nearly coincide: their split sqrt(D) amplifies the error
+  // of z by z / sqrt(D).
+  double z2 = z * z;
+  const double r = rcp_approx64(fma(3.0, z2, TINY - A));
+  z = fma(-fma(z2 - A, z, -ad), r, z);
+  z2 = z * z;
+  z = fma(-fma(z2 - A, z, -ad), r, z);
+  const double D = fabs(fma(-3.0 * z, z, 4.0 * A)) + TINY; // (v - u)^2
+  const double rs = rsqrt_approx64(D);
+  double x = D * rs;
+  x = fma(0.5 * rs, fma(-x, x, D), x);                     // sqrt(D): one Heron step, 2^-40
+  // roots of the |det| problem: u = -(z + x)/2 <= v = (x - z)/2 <= z; det < 0 mirrors them
+  const bool neg = det < 0.0;
+  const double sg = neg ? -1.0 : 1.0, hs = neg ? -0.5 : 0.5;
+  const double ez = fma(sg, z, shift), ev_ = fma(hs, x - z, shift), eu = fma(-hs, z + x, shift);
+  ev[0] = neg ? ez : eu;
+  ev[1] = ev_;
+  ev[2] = neg ? eu : ez;
+}
+
 // Eigenvalues only, in the requested order (0 increasing, 1 decreasing).
-__device__ __forceinline__ void sym3_eigenvalues(const Sym3d &m, int order, double ev[3]) {
+__device__ __forceinline__ void sym3_eigenvalues_closed_form(const Sym3d &m, int order, double ev[3]) {
   Sym3d s;
   double shift, scale;
   sym3_roots(m, s, shift, scale, ev);
   for (int d = 0; d < 3; d++) ev[d] = ev[d] * scale + shift;
   if ((order == 0 && ev[0] > ev[2]) || (order == 1 && ev[0] < ev[2])) {
+    double t = ev[0]; ev[0] = ev[2]; ev[2] = t;
+  }
+}
+__device__ __forceinline__ void sym3_eigenvalues(const Sym3d &m, int order, double ev[3]) {
+  sym3_eigenvalues_newton(m, ev);   // ascending
+  // decreasing order = first and last exchanged, the middle one stays (eigen3_simple.hpp:252-264)
+  if (order == 1) {
     double t = ev[0]; ev[0] = ev[2]; ev[2] = t;
   }
 }
