@@ -228,6 +228,40 @@ __device__ __forceinline__ void sym3_eigen_first(const Sym3d &m, int order, doub
   }
 }
 
+// The eigenvector that DiagonalizeSym3 returns FIRST (largest eigenvalue for decreasing order, smallest for
+// increasing), without the closed form: eigenvalue by sym3_eigenvalues_newton, then extract_kernel3's
+// construction (eigen3_simple.hpp:88-133) on m - lambda I -- the column with the largest diagonal entry crossed
+// with the other two, the longer product normalised (1/sqrt by MUFU.RSQ64H and one Newton step).  Branch-free,
+// no local arrays.  Used for the ~5 % of voxels that vote; where the eigenvalue is not separated the vector is
+// as arbitrary as the reference's.
+__device__ __forceinline__ void sym3_first_eigenvector_newton(const Sym3d &m, int order, double first[3]) {
+  double ev[3];
+  sym3_eigenvalues_newton(m, ev);
+  const double lam = order == 1 ? ev[2] : ev[0];
+  const double xx = m.xx - lam, yy = m.yy - lam, zz = m.zz - lam;
+  const double ax = fabs(xx), ay = fabs(yy), az = fabs(zz);
+  const bool use_z = az > fmax(ax, ay), use_y = !use_z && ay > ax;   // first maximum wins, as the reference's loop
+  // rep = column i0, a = column i0+1, b = column i0+2 (cyclic)
+  const double c0[3] = {xx, m.xy, m.xz}, c1[3] = {m.xy, yy, m.yz}, c2[3] = {m.xz, m.yz, zz};
+  double rep[3], a[3], b[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    rep[d] = use_z ? c2[d] : (use_y ? c1[d] : c0[d]);
+    a[d] = use_z ? c0[d] : (use_y ? c2[d] : c1[d]);
+    b[d] = use_z ? c1[d] : (use_y ? c0[d] : c2[d]);
+  }
+  double p[3], q[3];
+  cross3d(rep, a, p);
+  cross3d(rep, b, q);
+  const double np = dot3d(p, p), nq = dot3d(q, q);
+  const bool take_p = np > nq;
+  const double n = (take_p ? np : nq) + 1e-300;
+  double y = rsqrt_approx64(n);
+  y = y * fma(-0.5 * n, y * y, 1.5);
+#pragma unroll
+  for (int d = 0; d < 3; d++) first[d] = (take_p ? p[d] : q[d]) * y;
+}
+
 // ScoreHessianPlanar / Linear (feature.hpp:1529-1581) and ScoreTensorPlanar / Linear
 // (:1593-1612) from the FLOAT eigenvalues, evaluated in double, returned as float.
 __device__ __forceinline__ float score_from_eivals(const double ev[3], int score_kind,

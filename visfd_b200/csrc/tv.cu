@@ -38,7 +38,6 @@
 namespace visfd_cuda {
 
 constexpr int BR = 8;            // edge of a receiver tile and of the regions the list kernels work on
-constexpr int BR3 = BR * BR * BR;
 constexpr int VSH = 2;           // voters are ordered by bricks of edge 1 << VSH = 4: a receiver patch tests
 constexpr int VBR = 1 << VSH;    // the voters of the bricks that touch its reach, and 4^3 bricks hug a
                                  // radius-20 sphere better than 8^3 ones (72 % instead of 53 % accepted)
@@ -108,87 +107,56 @@ struct VoterSrc {
   float thr;
   int nx, ny;
   i64 nz;  // slab planes
-  int nbx, nby, nbz;     // 8^3 regions (one per CTA slot of the list kernels)
   int vbx, vby, vbz;     // 4^3 voter bricks: the order of the list, the index of counts[] / off[]
 };
 
-__device__ __forceinline__ bool is_voter(const VoterSrc &v, int x, int y, i64 z, float &w) {
-  if (x >= v.nx || y >= v.ny || z >= v.nz) return false;
-  i64 i = (z * v.ny + y) * (i64)v.nx + x;
-  float s = __ldg(v.sal + i);
-  if (!(s >= v.thr) || s == 0.0f) return false;  // cut: handlers.cpp:1792; skip: feature.hpp:2268
-  if (v.mask_src) {
-    float m = __ldg(v.mask_src + i);
-    if (m == 0.0f) return false;                 // feature.hpp:2259-2260
-    s *= m;                                      // a weight multiplies the decay, :2261-2265
-  }
-  w = s;
-  return true;
-}
+// The list kernels stream the saliency (and mask) volume by ROWS: a warp owns 8 consecutive bricks of one brick
+// row -- 32 columns x 4 rows x 4 planes -- and issues its sixteen 128-byte row loads back to back before it
+// looks at any of them (16 independent, fully coalesced loads per lane in flight; the round-1 kernels walked
+// 8^3 regions with 32-byte row pieces and reached 1.2 TB/s).  Lane = x column; the nibble of a ballot that
+// belongs to a brick gives its voters of that row, so counts and ranks in (z, y, x) order are popcounts.
+constexpr int VL_WARPS = 8;                 // warps per CTA, side by side along x: 1 KB of every row
+constexpr int VL_ROWS = VBR * VBR;          // 16 rows (y, z) per brick row
 
-// One CTA (512 threads = one thread per voxel of a brick) per run of VB consecutive bricks: the VB loads of
-// a thread are independent, so a CTA has VB times the bytes in flight of a one-brick CTA (which spent its
-// life waiting for a single load), and consecutive bricks are neighbours in x: 256-byte rows per warp.
-constexpr int VB = 8;
-
-struct BrickPos {
-  int bx, by, bz;
-};
-__device__ __forceinline__ BrickPos brick_pos(const VoterSrc &v, i64 b) {
-  BrickPos p;
-  p.bx = (int)(b % v.nbx);
-  const i64 r = b / v.nbx;
-  p.by = (int)(r % v.nby);
-  p.bz = (int)(r / v.nby);
-  return p;
-}
-__device__ __forceinline__ void next_brick(const VoterSrc &v, BrickPos &p) {
-  if (++p.bx == v.nbx) {
-    p.bx = 0;
-    if (++p.by == v.nby) { p.by = 0; p.bz++; }
-  }
-}
-
-// Voter brick of (region, sub-brick sb = sz*4 + sy*2 + sx), or -1 outside the brick grid
-__device__ __forceinline__ i64 voter_brick(const VoterSrc &v, const BrickPos &p, int sb) {
-  const int bx = 2 * p.bx + (sb & 1), by = 2 * p.by + ((sb >> 1) & 1), bz = 2 * p.bz + (sb >> 2);
-  if (bx >= v.vbx || by >= v.vby || bz >= v.vbz) return -1;
-  return ((i64)bz * v.vby + by) * v.vbx + bx;
-}
-
-// thread t of a region: x = t & 7, y = (t >> 3) & 7, z = t >> 6, so a warp holds one z and four y of one
-// half (y < 4 or y >= 4) and its lanes split into the x < 4 and x >= 4 sub-bricks
-constexpr unsigned X_LO = 0x0f0f0f0fu, X_HI = 0xf0f0f0f0u;
-__device__ __forceinline__ int warp_sub_brick(int w) { return ((w >> 3) << 2) | ((w & 1) << 1); }  // + sx
-
-__global__ void __launch_bounds__(BR3) voter_count_kernel(VoterSrc v, i64 n_regions, uint32_t *__restrict__ counts) {
-  __shared__ uint32_t cnt[VB][8];
-  const int t = threadIdx.x;
-  if (t < VB * 8) cnt[t >> 3][t & 7] = 0;
-  __syncthreads();
-  const i64 b0 = (i64)blockIdx.x * VB;
-  BrickPos bp = brick_pos(v, b0);
-  bool p[VB];
+struct VoterRows {
+  float s[VL_ROWS];       // saliency * mask weight, or 0 where the voxel is no voter
+  __device__ __forceinline__ void load(const VoterSrc &v, int x, int by, int bz) {
+    float m[VL_ROWS];
 #pragma unroll
-  for (int k = 0; k < VB; k++) {
-    float w;
-    p[k] = (b0 + k < n_regions) && is_voter(v, bp.bx * BR + (t & 7), bp.by * BR + ((t >> 3) & 7), (i64)bp.bz * BR + (t >> 6), w);
-    next_brick(v, bp);
-  }
-  const int sb = warp_sub_brick(t >> 5);
+    for (int r = 0; r < VL_ROWS; r++) {
+      const int y = by * VBR + (r & 3);
+      const i64 z = (i64)bz * VBR + (r >> 2);
+      const bool in = x < v.nx && y < v.ny && z < v.nz;
+      const i64 i = (z * v.ny + y) * (i64)v.nx + x;
+      s[r] = in ? __ldg(v.sal + i) : 0.0f;
+      m[r] = (in && v.mask_src) ? __ldg(v.mask_src + i) : 1.0f;
+    }
 #pragma unroll
-  for (int k = 0; k < VB; k++) {
-    const unsigned bal = __ballot_sync(0xffffffffu, p[k]);
-    if ((t & 31) == 0 && bal) {
-      if (bal & X_LO) atomicAdd(&cnt[k][sb], (uint32_t)__popc(bal & X_LO));
-      if (bal & X_HI) atomicAdd(&cnt[k][sb + 1], (uint32_t)__popc(bal & X_HI));
+    for (int r = 0; r < VL_ROWS; r++) {
+      // cut: handlers.cpp:1792; zero saliency never votes: feature.hpp:2268; masked voxels: :2259-2260;
+      // a mask weight multiplies the decay, :2261-2265
+      const bool voter = (s[r] >= v.thr) && s[r] != 0.0f && m[r] != 0.0f;
+      s[r] = voter ? (v.mask_src ? s[r] * m[r] : s[r]) : 0.0f;
     }
   }
-  __syncthreads();
-  if (t < VB * 8 && b0 + (t >> 3) < n_regions) {
-    const i64 vb = voter_brick(v, brick_pos(v, b0 + (t >> 3)), t & 7);
-    if (vb >= 0) counts[vb] = cnt[t >> 3][t & 7];
+  // (a voter whose weighted saliency is exactly 0 cannot occur: both factors are non-zero floats, and a
+  // product that underflows to 0 would vote with weight 0 anyway)
+};
+
+__global__ void __launch_bounds__(32 * VL_WARPS) voter_count_kernel(VoterSrc v, uint32_t *__restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int bx0 = (blockIdx.x * VL_WARPS + (threadIdx.x >> 5)) * 8;
+  if (bx0 >= v.vbx) return;
+  const int by = blockIdx.y, bz = blockIdx.z;
+  VoterRows rows;
+  rows.load(v, bx0 * VBR + lane, by, bz);
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int r = 0; r < VL_ROWS; r++) {
+    const unsigned bal = __ballot_sync(0xffffffffu, rows.s[r] != 0.0f);
+    cnt += __popc((bal >> (lane & 28)) & 15u);
   }
+  if ((lane & 3) == 0 && bx0 + (lane >> 2) < v.vbx) counts[((i64)bz * v.vby + by) * v.vbx + bx0 + (lane >> 2)] = cnt;
 }
 
 // Exclusive scan of n uint32 counters into off[0..n] (off[n] = total): per-block scan,
@@ -326,71 +294,51 @@ __device__ __forceinline__ void voter_direction(const DirSrc &d, int nx, int ny,
 #undef F
   Sym3d m = {hxx, hyy, hzz, __fmul_rn(__fmul_rn(0.25f, xy), s2), __fmul_rn(__fmul_rn(0.25f, yz), s2),
              __fmul_rn(__fmul_rn(0.25f, xz), s2)};
-  double ev[3], e0[3];
-  sym3_eigen_first(m, d.order, ev, e0);
+  double e0[3];
+  sym3_first_eigenvector_newton(m, d.order, e0);
   n[0] = (float)e0[0];
   n[1] = (float)e0[1];
   n[2] = (float)e0[2];
 }
 
-// Pass 1 of the fill (one CTA per run of VB bricks): positions and weights in brick order, voxels of a
-// brick in thread order (z, y, x).
-__global__ void __launch_bounds__(BR3, 2)
-voter_fill_kernel(VoterSrc v, i64 n_regions, const uint32_t *__restrict__ off, float inv_total, bool lut,
+// Pass 1 of the fill: positions and weights in brick order, voxels of a brick in (z, y, x) order.
+__global__ void __launch_bounds__(32 * VL_WARPS)
+voter_fill_kernel(VoterSrc v, const uint32_t *__restrict__ off, float inv_total, bool lut,
                   VoterRec *__restrict__ rec, uint32_t *__restrict__ nonpos_flag) {
-  __shared__ uint32_t wsum[VB][2][BR3 / 32];   // per region, x half, warp
-  const i64 b0 = (i64)blockIdx.x * VB;
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int nb = (int)min((i64)VB, n_regions - b0);
-  const int tx = t & 7, ty = (t >> 3) & 7, tz = t >> 6;
-  BrickPos bp = brick_pos(v, b0);
-  unsigned mine = 0;   // bit k: this thread's voxel of region k votes
-  float wt[VB];
+  const int lane = threadIdx.x & 31;
+  const int bx0 = (blockIdx.x * VL_WARPS + (threadIdx.x >> 5)) * 8;
+  if (bx0 >= v.vbx) return;
+  const int by = blockIdx.y, bz = blockIdx.z;
+  const int x = bx0 * VBR + lane;
+  VoterRows rows;
+  rows.load(v, x, by, bz);
+  const int bx = bx0 + (lane >> 2);
+  const uint32_t base = (bx < v.vbx) ? __ldg(off + ((i64)bz * v.vby + by) * v.vbx + bx) : 0u;
+  const unsigned below = (1u << (lane & 3)) - 1u;   // lanes of my nibble that come before me
+  uint32_t rank = 0;                                 // voters of my brick in the rows done so far
 #pragma unroll
-  for (int k = 0; k < VB; k++) {
-    wt[k] = 0.0f;
-    if (k < nb && is_voter(v, bp.bx * BR + tx, bp.by * BR + ty, (i64)bp.bz * BR + tz, wt[k])) mine |= 1u << k;
-    next_brick(v, bp);
-  }
-  const unsigned half = (tx < 4) ? X_LO : X_HI;
-  unsigned bal[VB];
-#pragma unroll
-  for (int k = 0; k < VB; k++) {
-    bal[k] = __ballot_sync(0xffffffffu, (mine >> k) & 1u);
-    if (lane == 0) {
-      wsum[k][0][w] = __popc(bal[k] & X_LO);
-      wsum[k][1][w] = __popc(bal[k] & X_HI);
-    }
-  }
-  __syncthreads();
-  if (!mine) return;
-  const int sb = warp_sub_brick(w) + (tx >> 2);
-  bp = brick_pos(v, b0);
-#pragma unroll
-  for (int k = 0; k < VB; k++) {
-    if ((mine >> k) & 1u) {
-      // rank inside the 4^3 brick in (z, y, x) order: the warps of the same z half and y half that come first
-      uint32_t rank = __popc(bal[k] & half & ((1u << lane) - 1u));
-      for (int q = (w & ~7) | (w & 1); q < w; q += 2) rank += wsum[k][tx >> 2][q];
-      const float wgt = wt[k] * inv_total;
+  for (int r = 0; r < VL_ROWS; r++) {
+    const unsigned nib = (__ballot_sync(0xffffffffu, rows.s[r] != 0.0f) >> (lane & 28)) & 15u;
+    if (rows.s[r] != 0.0f) {
+      const float wgt = rows.s[r] * inv_total;
       if (!(wgt > 0.0f)) *nonpos_flag = 1u;  // benign race: every writer stores the same value
       // the three forms of the weight the gather kernels fold into their arithmetic (vote())
       const float w4 = 4.0f * wgt, l4 = log2f(w4);
-      VoterRec *r = rec + off[voter_brick(v, bp, sb)] + rank;
-      const float px = -(float)(bp.bx * BR + tx), py = -(float)(bp.by * BR + ty), pz = -(float)(bp.bz * BR + tz);
+      VoterRec *q = rec + base + rank + __popc(nib & below);
+      const float px = -(float)x, py = -(float)(by * VBR + (r & 3)), pz = -(float)(bz * VBR + (r >> 2));
       if (lut) {   // only used when every weight is positive (checked by the host before the launch)
         const float lam = (float)pow((double)fmaxf(w4, 0.0f), 1.0 / 6.0);
         const float rho = pow2f(LUT_RHO_LOG2);
-        r->a = make_float4(px * rho, py * rho, pz * rho, lam * lam * pow2f(LUT_K_LOG2));
-        r->b.w = lam;
-        r->c.w = 0.0f;
+        q->a = make_float4(px * rho, py * rho, pz * rho, lam * lam * pow2f(LUT_K_LOG2));
+        q->b.w = lam;
+        q->c.w = 0.0f;
       } else {
-        r->a = make_float4(px, py, pz, 0.5f * l4);
-        r->b.w = l4;
-        r->c.w = w4;
+        q->a = make_float4(px, py, pz, 0.5f * l4);
+        q->b.w = l4;
+        q->c.w = w4;
       }
     }
-    next_brick(v, bp);
+    rank += __popc(nib);
   }
 }
 
@@ -971,12 +919,13 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   DecayInfo info = decay_info(p.sigma, hw);
   VREQUIRE((int)info.shell_keep.size() <= TV_MAX_SHELL, "too many lattice points on the support shell");
 
-  const int nbx = (int)div_up(nx, BR), nby = (int)div_up(ny, BR), nbz = (int)div_up(nz_local, BR);
-  const i64 n_regions = (i64)nbx * nby * nbz;
+  const int nbx = (int)div_up(nx, BR), nby = (int)div_up(ny, BR);   // 8x8 receiver tiles per layer
   const int vbx = (int)div_up(nx, VBR), vby = (int)div_up(ny, VBR), vbz = (int)div_up(nz_local, VBR);
   const i64 n_bricks = (i64)vbx * vby * vbz;
   VREQUIRE(n_bricks < 2147483647LL, "too many bricks for one launch");
-  VoterSrc vs{saliency, mask_src, thr, (int)nx, (int)ny, nz_local, nbx, nby, nbz, vbx, vby, vbz};
+  VREQUIRE(vby <= 65535 && vbz <= 65535, "slab too large for the voter list kernels");
+  VoterSrc vs{saliency, mask_src, thr, (int)nx, (int)ny, nz_local, vbx, vby, vbz};
+  const dim3 vl_grid((unsigned)div_up(vbx, 8 * VL_WARPS), (unsigned)vby, (unsigned)vbz);
 
   Scratch<uint32_t> counts(ctx, n_bricks), off(ctx, n_bricks + 1);
   const i64 n_scan_blocks = (n_bricks + SCAN_B - 1) / SCAN_B;
@@ -991,7 +940,7 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   Scratch<VoterRec> rec;
   {
     StageTimer t(ctx, "compact");
-    voter_count_kernel<<<(unsigned)div_up(n_regions, VB), BR3, 0, ctx->stream>>>(vs, n_regions, counts.get());
+    voter_count_kernel<<<vl_grid, 32 * VL_WARPS, 0, ctx->stream>>>(vs, counts.get());
     VCK(cudaGetLastError());
     scan_local_kernel<<<(unsigned)n_scan_blocks, SCAN_T, 0, ctx->stream>>>(counts.get(), off.get(), sums.get(), n_bricks);
     VCK(cudaGetLastError());
@@ -1009,8 +958,8 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
       DirSrc ds{direction, smoothed, ridge_sigma, eival_order, z_offset, nz_global};
       VCK(cudaMemsetAsync(sums.get() + n_scan_blocks + 1, 0, sizeof(uint32_t), ctx->stream));
       for (;;) {
-        voter_fill_kernel<<<(unsigned)div_up(n_regions, VB), BR3, 0, ctx->stream>>>(
-            vs, n_regions, off.get(), 1.0f / info.total, use_lut, rec.get(), sums.get() + n_scan_blocks + 1);
+        voter_fill_kernel<<<vl_grid, 32 * VL_WARPS, 0, ctx->stream>>>(vs, off.get(), 1.0f / info.total, use_lut, rec.get(),
+                                                                      sums.get() + n_scan_blocks + 1);
         VCK(cudaGetLastError());
         ctx->count_launch();
         VCK(cudaMemcpyAsync(&nonpos, sums.get() + n_scan_blocks + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -1106,8 +1055,8 @@ bool tv_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 n
   }
   if (use_lut && n_voters > 0 && !lut_mode) {
     // records were written for the table kernel but no table fits: rewrite them for the MUFU kernel
-    voter_fill_kernel<<<(unsigned)div_up(n_regions, VB), BR3, 0, ctx->stream>>>(
-        vs, n_regions, off.get(), 1.0f / info.total, false, rec.get(), sums.get() + n_scan_blocks + 1);
+    voter_fill_kernel<<<vl_grid, 32 * VL_WARPS, 0, ctx->stream>>>(vs, off.get(), 1.0f / info.total, false, rec.get(),
+                                                                  sums.get() + n_scan_blocks + 1);
     VCK(cudaGetLastError());
     DirSrc ds{direction, smoothed, ridge_sigma, eival_order, z_offset, nz_global};
     voter_direction_kernel<<<div_up(n_voters, 256), 256, 0, ctx->stream>>>(ds, (int)nx, (int)ny, n_voters, false, rec.get());
