@@ -299,6 +299,26 @@ int visfd_cuda_label_connected(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t n
                                float threshold_tensor_saliency, float threshold_tensor_neighbor, int64_t *labels,
                                int64_t *n_clusters, float *cluster_maxima, int64_t maxima_capacity, int64_t *n_maxima);
 
+/* ---- oriented point cloud of a detected surface ---------------------------------------
+ * The block of HandleTV that runs when `-normals-file` is given (bin/filter_mrc/handlers.cpp:2039-2309; the
+ * reference has no function for it).  For every un-masked voxel whose label equals select_cluster (`labels` =
+ * tomo_out after LabelConnected, a float image as in the reference; `-select-cluster`, settings.cpp:3171):
+ * follow the unit surface normal (`direction`, N*3) in both directions in steps of curve_ds
+ * (`settings.surface_normal_curve_ds`, 0.2) while inside the cluster, take the saliency-weighted mean position
+ * (:2097-2215), then move it onto the ridge of the saliency along the eigenvector of the saliency's
+ * finite-difference Hessian with the largest |eigenvalue| (`surface_find_ridge`, :2224-2295), dropping points
+ * further than max_distance voxels from the ridge (`max_distance_to_feature`, 1.3; <= 0 disables the test).
+ * labels == NULL: every un-masked voxel with its position times voxel_width and its direction (:2053-2066).
+ * rows: capacity x {x, y, z, nx, ny, nz} in the reference's order (raster order of the source voxel), positions
+ * times voxel_width when the ridge step ran (:2283-2285) and in voxels otherwise, normals scaled by the saliency
+ * of the source voxel; *n_points = number found (rows beyond capacity are not stored): the columns of the PLY
+ * file WriteOrientedPointCloudPLY writes (bin/filter_mrc/file_io.hpp:501-527).  A walk over a zero direction,
+ * endless in the reference, stops after 4 (nx+ny+nz) / curve_ds steps.  DEVICE or HOST pointers. */
+int visfd_cuda_surface_points(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *saliency,
+                              const float *direction, const float *labels, const float *mask, int select_cluster,
+                              const float voxel_width[3], float curve_ds, int find_ridge, float max_distance,
+                              float *rows, int64_t capacity, int64_t *n_points);
+
 /* ---- bookkeeping for benchmarks (no reference counterpart) ------------------------- */
 /* Enable/disable the per-stage CUDA-event timing behind visfd_cuda_stage_ms. */
 void visfd_cuda_set_timing(visfd_ctx *ctx, int enabled);

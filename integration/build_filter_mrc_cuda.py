@@ -19,7 +19,8 @@ patched sources still build the stock program without the define.
   * HandleBinning: BinArray3D -> visfd_cuda::BinArray3D
   * HandleTV: lines 1618-1892 (CalcHessian, eigen loop, cut, TVDenseStick, score loop) replaced by ONE call,
     visfd_cuda::MembranePipeline, unless the run subtracts a background, loads saved tensors or detects
-    edges or curves; the clustering call becomes visfd_cuda::LabelConnected
+    edges or curves; the clustering call becomes visfd_cuda::LabelConnected; the loop that collects the oriented
+    point cloud of -normals-file (2050-2299) becomes visfd_cuda::SurfacePointCloud
   * HandleLabelConnected: visfd_cuda::LabelConnected
   * feature_variants.hpp (BlobDogNM): BlobDogD -> visfd_cuda::BlobDogD
 
@@ -112,6 +113,19 @@ def patch_handlers(t):
              after="float ****aaaafVoteTensor = hessian_tensor.aaaafI;", what="voting")
     t = edit(t, "      LabelConnected(image_size, //image size", "      VISFD_NS::LabelConnected(image_size, //image size",
              after=tv, what="clustering in HandleTV")
+    # the point cloud of -normals-file: one call instead of the loop over the voxels (handlers.cpp:2050-2299)
+    t = edit(t, "    for (int iz = 0; iz < image_size[2]; ++iz) {\n      for (int iy = 0; iy < image_size[1]; ++iy) {\n"
+                "        for (int ix = 0; ix < image_size[0]; ++ix) {\n          if (mask.aaafI && (mask.aaafI[iz][iy][ix] == 0.0))",
+             "#ifdef VISFD_USE_CUDA\n"
+             "    cerr << \"-- surface point cloud on the GPU (libvisfd_cuda) --\" << endl;\n"
+             "    visfd_cuda::SurfacePointCloud(image_size, aaafSaliency, aaaafDirection, aaafVoxel2Cluster, mask.aaafI,\n"
+             "                                  settings.select_cluster, voxel_width, settings.surface_normal_curve_ds,\n"
+             "                                  settings.surface_find_ridge, settings.max_distance_to_feature, crds, norms);\n"
+             "    if (false)\n"
+             "#endif\n"
+             "    for (int iz = 0; iz < image_size[2]; ++iz) {\n      for (int iy = 0; iy < image_size[1]; ++iy) {\n"
+             "        for (int ix = 0; ix < image_size[0]; ++ix) {\n          if (mask.aaafI && (mask.aaafI[iz][iy][ix] == 0.0))",
+             after="aaafVoxel2Cluster = tomo_out.aaafI; //tomo_out was filled by LabelConnected()", what="point cloud")
     t = edit(t, "    LabelConnected(tomo_in.header.nvoxels, //image size",
              "    VISFD_NS::LabelConnected(tomo_in.header.nvoxels, //image size", what="HandleLabelConnected")
     t = edit(t, "  BinArray3D(tomo_in.header.nvoxels,", "  VISFD_NS::BinArray3D(tomo_in.header.nvoxels,", what="HandleBinning")

@@ -237,6 +237,22 @@ class Oracle:
             return labels, int(n), dire
         return labels, int(n)
 
+    def surface_points(self, saliency, direction, labels=None, mask=None, select_cluster=1, voxel_width=(1.0, 1.0, 1.0),
+                       curve_ds=0.2, find_ridge=True, max_distance=1.3, capacity=None):
+        """The oriented point cloud HandleTV writes with -normals-file (handlers.cpp:2039-2309): rows
+        {x, y, z, nx, ny, nz} in raster order of the source voxel (restatement only: the reference code is inline in
+        HandleTV; pinned on the stock binary's PLY files)."""
+        if self.kind != "port":
+            raise RuntimeError("surface_points: only the restatement has this entry")
+        sal, dire, lab, mask = _f32(saliency), _f32(direction), _f32(labels), _f32(mask)
+        cap = int(capacity if capacity is not None else sal.size)
+        rows = np.zeros((cap, 6), np.float32)
+        vw = (C.c_float * 3)(*[float(v) for v in voxel_width])
+        n = self._fn("surface_points", _i64)(*self._dims(sal.shape), _ptr(sal), _ptr(dire), _ptr(lab), _ptr(mask),
+                                            _i(select_cluster), vw, _f(curve_ds), _i(int(find_ridge)), _f(max_distance),
+                                            _ptr(rows), _i64(cap))
+        return rows[:min(int(n), cap)], int(n)
+
     # ---- thresholds ----------------------------------------------------------
     def threshold1(self, a, thr, outA=0.0, outB=1.0):
         a = _f32(a)

@@ -24,6 +24,7 @@
 #include <cstring>
 #include <cmath>
 #include <algorithm>
+#include <array>
 #include <functional>
 #include <queue>
 #include <tuple>
@@ -1239,6 +1240,136 @@ i64 vo_label_connected(i64 nx, i64 ny, i64 nz, const float *sal, const float *ma
   }
   if (direction_out) memcpy(direction_out, dir.data(), sizeof(float) * 3 * (size_t)N);
   return n_clusters;
+}
+
+
+// ---- oriented point cloud of a detected surface (bin/filter_mrc/handlers.cpp:2039-2309) -----------------------
+// For every un-masked voxel of the selected cluster: (1) follow the surface normal in both directions while
+// inside the cluster (step ds), take the saliency-weighted mean arc length and the sample next to it (:2097-2215);
+// (2) move that point onto the ridge of the saliency along the eigenvector of the saliency's finite-difference
+// Hessian with the largest |eigenvalue| (:2224-2295); points further than max_distance from the ridge, with a
+// vanishing gradient component, or outside the image are dropped.  labels == NULL: every un-masked voxel, position
+// x voxel width, normal = direction (:2053-2066).  rows: {x, y, z, nx, ny, nz} in raster order of the source voxel;
+// returns the number of points (only the first `capacity` are stored).
+// Deviations, both below the 6 digits the reference prints: the 3x3 eigen-decomposition of the float Hessian is
+// done in double (the reference instantiates DiagonalizeSym3 with float here), and a rounded sample position
+// that an extrapolation pushed outside the image is clamped (the reference reads out of bounds).
+i64 vo_surface_points(i64 nx, i64 ny, i64 nz, const float *sal, const float *dir, const float *labels,
+                      const float *mask, int select_cluster, const float voxel_width[3], float ds, int find_ridge,
+                      float max_distance, float *rows, i64 capacity) {
+  i64 n_out = 0;
+  const int size[3] = {(int)nx, (int)ny, (int)nz};
+  auto emit = [&](const float xyz[3], const float nrm[3]) {
+    if (n_out < capacity) {
+      for (int d = 0; d < 3; d++) { rows[6 * n_out + d] = xyz[d]; rows[6 * n_out + 3 + d] = nrm[d]; }
+    }
+    n_out++;
+  };
+  auto inside = [&](const int p[3]) { return p[0] >= 0 && p[0] < size[0] && p[1] >= 0 && p[1] < size[1] && p[2] >= 0 && p[2] < size[2]; };
+  auto unit = [&](i64 i, float u[3]) {
+    const float *v = dir + 3 * i;
+    float norm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);   // length3, visfd_utils.hpp:40-43
+    for (int d = 0; d < 3; d++) u[d] = v[d] / norm;
+  };
+  for (int iz = 0; iz < size[2]; iz++)
+    for (int iy = 0; iy < size[1]; iy++)
+      for (int ix = 0; ix < size[0]; ix++) {
+        const i64 i0 = IDX(ix, iy, iz);
+        if (mask && mask[i0] == 0.0f) continue;
+        float xyz[3], normal[3];
+        if (!labels) {
+          xyz[0] = ix * voxel_width[0]; xyz[1] = iy * voxel_width[1]; xyz[2] = iz * voxel_width[2];
+          for (int d = 0; d < 3; d++) normal[d] = dir[3 * i0 + d];
+          emit(xyz, normal);
+          continue;
+        }
+        if ((float)select_cluster != labels[i0]) continue;
+        xyz[0] = ix; xyz[1] = iy; xyz[2] = iz;
+        unit(i0, normal);
+        for (int d = 0; d < 3; d++) normal[d] *= sal[i0];
+        if (ds > 0.0f) {
+          std::vector<float> vS, vW, bS, bW;
+          std::vector<std::array<float, 3> > vX, bX;
+          std::array<float, 3> r = {(float)ix, (float)iy, (float)iz};
+          int p[3] = {ix, iy, iz};
+          float s = 0.0f, drds[3];
+          // (a zero or NaN direction would keep the reference walking on the spot for ever; bounded here)
+          const size_t max_steps = (size_t)(4.0 * (nx + ny + nz) / ds) + 16;
+          while (vS.size() < max_steps && inside(p) && !(mask && mask[IDX(p[0], p[1], p[2])] == 0.0f) && labels[IDX(p[0], p[1], p[2])] == labels[i0]) {
+            const i64 j = IDX(p[0], p[1], p[2]);
+            vS.push_back(s); vX.push_back(r); vW.push_back(sal[j]);
+            unit(j, drds);
+            s += ds;
+            for (int d = 0; d < 3; d++) { r[d] += ds * drds[d]; p[d] = (int)std::round(r[d]); }
+          }
+          r = {(float)ix, (float)iy, (float)iz};
+          p[0] = ix; p[1] = iy; p[2] = iz;
+          s = 0.0f;
+          while (bS.size() < max_steps) {
+            unit(IDX(p[0], p[1], p[2]), drds);
+            s -= ds;
+            for (int d = 0; d < 3; d++) { r[d] -= ds * drds[d]; p[d] = (int)std::round(r[d]); }
+            if (!inside(p)) break;
+            const i64 j = IDX(p[0], p[1], p[2]);
+            if (mask && mask[j] == 0.0f) break;
+            if (labels[j] != labels[i0]) break;
+            bS.push_back(s); bX.push_back(r); bW.push_back(sal[j]);
+          }
+          vS.insert(vS.begin(), bS.rbegin(), bS.rend());
+          vX.insert(vX.begin(), bX.rbegin(), bX.rend());
+          vW.insert(vW.begin(), bW.rbegin(), bW.rend());
+          float sum_s = 0.0f, sum_w = 0.0f;
+          for (size_t k = 0; k < vS.size(); k++) { sum_s += vW[k] * vS[k]; sum_w += vW[k]; }
+          const float ave_s = sum_s / sum_w;
+          size_t k = 0;
+          while (k + 1 < vS.size()) {
+            k++;
+            if (vS[k - 1] <= ave_s && ave_s <= vS[k]) break;
+          }
+          for (int d = 0; d < 3; d++) p[d] = std::min(std::max((int)std::round(vX[k][d]), 0), size[d] - 1);
+          unit(IDX(p[0], p[1], p[2]), normal);
+          for (int d = 0; d < 3; d++) {
+            if (k + 1 < vS.size()) xyz[d] = vX[k][d] + (vX[k + 1][d] - vX[k][d]) * ((ave_s - vS[k]) / (vS[k + 1] - vS[k]));
+            else xyz[d] = vX[k][d];
+            normal[d] *= sal[i0];
+          }
+        }
+        if (find_ridge) {
+          int q[3];
+          for (int d = 0; d < 3; d++) q[d] = std::min(std::max((int)std::round(xyz[d]), 0), size[d] - 1);
+          i64 x = q[0], y = q[1], z = q[2];
+          if (x == 0) x++; else if (x == nx - 1) x--;
+          if (y == 0) y++; else if (y == ny - 1) y--;
+          if (z == 0) z++; else if (z == nz - 1) z--;
+#define F(dx, dy, dz) sal[IDX(x + (dx), y + (dy), z + (dz))]
+          const float c = F(0, 0, 0);
+          const float g[3] = {0.5f * (F(1, 0, 0) - F(-1, 0, 0)), 0.5f * (F(0, 1, 0) - F(0, -1, 0)), 0.5f * (F(0, 0, 1) - F(0, 0, -1))};
+          const float hxx = F(1, 0, 0) + F(-1, 0, 0) - 2 * c, hyy = F(0, 1, 0) + F(0, -1, 0) - 2 * c, hzz = F(0, 0, 1) + F(0, 0, -1) - 2 * c;
+          const float hxy = 0.25f * (F(1, 1, 0) + F(-1, -1, 0) - F(1, -1, 0) - F(-1, 1, 0));
+          const float hyz = 0.25f * (F(0, 1, 1) + F(0, -1, -1) - F(0, 1, -1) - F(0, -1, 1));
+          const float hxz = 0.25f * (F(1, 0, 1) + F(-1, 0, -1) - F(-1, 0, 1) - F(1, 0, -1));
+#undef F
+          const double M[3][3] = {{hxx, hxy, hxz}, {hxy, hyy, hyz}, {hxz, hyz, hzz}};
+          double ev[3], E[3][3];
+          vo_diagonalize_sym3(M, ev, E, 0);                  // increasing; then DECREASING_ABS_EIVALS (:252-264)
+          if (std::fabs(ev[0]) < std::fabs(ev[2])) {
+            std::swap(ev[0], ev[2]);
+            for (int d = 0; d < 3; d++) std::swap(E[0][d], E[2][d]);
+          }
+          float v1[3] = {(float)E[0][0], (float)E[0][1], (float)E[0][2]};
+          const float l1 = (float)ev[0];
+          float along = g[0] * v1[0] + g[1] * v1[1] + g[2] * v1[2];
+          if (along < 0.0f) { along = -along; for (int d = 0; d < 3; d++) v1[d] = -v1[d]; }
+          else if (along == 0.0f) continue;
+          const float dist = (l1 != 0) ? along / l1 : INFINITY;
+          if (max_distance > 0.0f && std::fabs(dist) > max_distance) continue;
+          for (int d = 0; d < 3; d++) xyz[d] = q[d] - dist * v1[d];
+          if (xyz[0] < 0.0f || size[0] < xyz[0] || xyz[1] < 0.0f || size[1] < xyz[1] || xyz[2] < 0.0f || size[2] < xyz[2]) continue;
+          for (int d = 0; d < 3; d++) xyz[d] *= voxel_width[d];
+        }
+        emit(xyz, normal);
+      }
+  return n_out;
 }
 
 } // extern "C"

@@ -66,8 +66,15 @@ def test_membrane_detection_sh_through_the_cuda_cli(exe, golden, tmp_path):
     cli = golden["c1_connect_labels"]
     assert np.array_equal(out2, cli.astype(np.float32))
     assert int((out2 == 1).sum()) == 69
+    assert "surface point cloud on the GPU" in log
     ply = (tmp_path / "normals.ply").read_text().splitlines()
     assert "element vertex 58" in ply
+    # ... and they are the stock binary's 58 vertices (tests/golden/surface_points.npz), to the six digits of the file
+    rows = np.array([[float(v) for v in l.split()] for l in ply[ply.index("end_header") + 1:]], np.float64)
+    want_ply = np.load(os.path.join(ROOT, "tests", "golden", "surface_points.npz"))["c1_ply"].astype(np.float64)
+    assert rows.shape == want_ply.shape
+    den = np.maximum(np.abs(want_ply), 1e-3 * np.abs(want_ply).max(axis=0))
+    assert (np.abs(rows - want_ply) / den).max() <= 1e-4
     # ---- both passes in one run: pipeline, tensors and clustering all on the GPU ----
     log = run([exe] + base + ["-out", "both.rec", "-connect", "1e+09", "-connect-angle", "30"], tmp_path)
     assert "membrane pipeline on the GPU" in log and "Number of clusters found: 1" in log

@@ -358,6 +358,24 @@ class Context:
                                                   _ptr(dr)))
         return score, ev, dr
 
+    def surface_points(self, saliency, direction, labels=None, mask=None, select_cluster=1, voxel_width=(1.0, 1.0, 1.0),
+                       curve_ds=0.2, find_ridge=True, max_distance=1.3, capacity=None):
+        """The oriented point cloud of `-normals-file` (handlers.cpp:2039-2309) -> (rows [n, 6] numpy, n_found);
+        labels: float image (tomo_out after LabelConnected) or None for every un-masked voxel."""
+        direction = _prep(direction)
+        saliency, labels, mask = _prep(saliency), _prep(labels), _prep(mask)
+        shape = tuple(direction.shape[:-1])
+        nz, ny, nx = shape
+        cap = int(capacity if capacity is not None else nz * ny * nx)
+        rows = np.zeros((max(cap, 1), 6), np.float32)
+        n = C.c_int64(0)
+        vw = (C.c_float * 3)(*[float(v) for v in voxel_width])
+        self._ck(self.lib.visfd_cuda_surface_points(self.h, _i64(nx), _i64(ny), _i64(nz), _ptr(saliency), _ptr(direction),
+                                                    _ptr(labels), _ptr(mask), _i(int(select_cluster)), vw,
+                                                    C.c_float(curve_ds), _i(int(find_ridge)), C.c_float(max_distance),
+                                                    rows.ctypes.data_as(C.c_void_p), _i64(cap), C.byref(n)))
+        return rows[:min(n.value, cap)], int(n.value)
+
     # ---- clustering --------------------------------------------------------------------------------
     def label_connected(self, saliency, tensor, threshold_saliency, angle_deg=15.0, order=DECREASING_EIVALS,
                         mask=None, direction=None, want_direction=False, consider_dot_product_sign=False,

@@ -19,6 +19,7 @@
 //
 // There is no CPU fallback: a failed CUDA call throws.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -372,6 +373,37 @@ inline size_t LabelConnected(const int image_size[3], float const *const *const 
   if (pv_cluster_saliencies) pv_cluster_saliencies->clear();
   if (pReportProgress) *pReportProgress << "Number of clusters found: " << n_clusters << "\n";
   return (size_t)n_clusters;
+}
+
+// ---- oriented point cloud (`-normals-file`) -----------------------------------------------------
+// The loop of HandleTV that fills `crds` / `norms` for WriteOrientedPointCloudPLY (bin/filter_mrc/handlers.cpp:2039-2309;
+// the reference has no function for it, so the name is ours and the arguments are the variables of that block):
+// aaafVoxel2Cluster = tomo_out.aaafI after LabelConnected, or nullptr when the voxels were not clustered.
+inline void SurfacePointCloud(const int image_size[3], float const *const *const *aaafSaliency,
+                              std::array<float, 3> const *const *const *aaaafDirection,
+                              float const *const *const *aaafVoxel2Cluster, float const *const *const *aaafMask,
+                              int select_cluster, const float voxel_width[3], float surface_normal_curve_ds,
+                              bool surface_find_ridge, float max_distance_to_feature,
+                              std::vector<std::array<float, 3> > &crds, std::vector<std::array<float, 3> > &norms) {
+  Dense3<float, 1> sal(image_size, aaafSaliency, false), lab(image_size, aaafVoxel2Cluster, false), m(image_size, aaafMask, false);
+  Dense3<std::array<float, 3>, 3> dir(image_size, aaaafDirection, false);
+  const int64_t N = (int64_t)image_size[0] * image_size[1] * image_size[2];
+  int64_t n = 0, cap = 1 << 16;
+  std::vector<float> rows;
+  for (;;) {
+    rows.resize(6 * (size_t)cap);
+    Check(visfd_cuda_surface_points(Context(), image_size[0], image_size[1], image_size[2], sal.data(), dir.data(), lab.data(),
+                                    m.data(), select_cluster, voxel_width, surface_normal_curve_ds, surface_find_ridge ? 1 : 0,
+                                    max_distance_to_feature, rows.data(), cap, &n));
+    if (n <= cap) break;
+    cap = std::min<int64_t>(n, N);
+  }
+  crds.resize((size_t)n);
+  norms.resize((size_t)n);
+  for (size_t i = 0; i < (size_t)n; i++) {
+    crds[i] = {rows[6 * i], rows[6 * i + 1], rows[6 * i + 2]};
+    norms[i] = {rows[6 * i + 3], rows[6 * i + 4], rows[6 * i + 5]};
+  }
 }
 
 // TV3D<float, int, array<float,3>, float*>: feature.hpp:1631-2483
