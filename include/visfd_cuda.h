@@ -224,6 +224,15 @@ int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz,
                         const visfd_membrane_params *p, float *out, float *hess_saliency,
                         float *direction, float *tensor, float *threshold_out);
 
+/* The same with `-membrane-background` (settings.width_b > 0; handlers.cpp:1577-1592): both the ridge score
+ * (before the cut; :1698-1702) and the post-vote score (:1883-1887) are multiplied by peak_height =
+ * source - ApplyGauss(source, background_sigma, halfwidth floor(background_sigma * truncate_ratio), mask,
+ * normalize_near_boundaries).  background_sigma == 0: identical to visfd_cuda_membrane. */
+int visfd_cuda_membrane_background(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src,
+                                   const float *mask, const visfd_membrane_params *p, float background_sigma,
+                                   int normalize_near_boundaries, float *out, float *hess_saliency, float *direction,
+                                   float *tensor, float *threshold_out);
+
 /* Slab stages of the same pipeline for the multi-GPU driver (DEVICE pointers only).
  * A rank owns global planes [z_offset+own_z0, z_offset+own_z1) and holds a slab that
  * extends them by a halo of RAW SOURCE planes (exchanged once, before stage 1):

@@ -18,7 +18,7 @@ patched sources still build the stock program without the define.
   * HandleGauss / HandleDog / HandleLoGDoG: visfd:: -> visfd_cuda:: (same argument lists)
   * HandleBinning: BinArray3D -> visfd_cuda::BinArray3D
   * HandleTV: lines 1618-1892 (CalcHessian, eigen loop, cut, TVDenseStick, score loop) replaced by ONE call,
-    visfd_cuda::MembranePipeline, unless the run subtracts a background, loads saved tensors or detects
+    visfd_cuda::MembranePipeline (with `-membrane-background` too), unless the run loads saved tensors or detects
     edges or curves; the clustering call becomes visfd_cuda::LabelConnected; the loop that collects the oriented
     point cloud of -normals-file (2050-2299) becomes visfd_cuda::SurfacePointCloud
   * HandleLabelConnected: visfd_cuda::LabelConnected
@@ -61,9 +61,6 @@ SHIM_INCLUDE = """using namespace visfd;
 """
 
 FUSED = """#ifdef VISFD_USE_CUDA
-  visfd_fused = (! subtract_background) &&
-                (settings.load_intermediate_fname_base == "") &&
-                (settings.filter_type == Settings::SURFACE_RIDGE);
   if (visfd_fused) {
     visfd_membrane_params p;
     p.sigma           = sigma;
@@ -81,7 +78,9 @@ FUSED = """#ifdef VISFD_USE_CUDA
     cerr << "-- membrane pipeline on the GPU (libvisfd_cuda) --" << endl;
     visfd_cuda::MembranePipeline(image_size, tomo_in.aaafI, tomo_out.aaafI, mask.aaafI, p,
                                  aaaafGradient,  // = aaaafDirection below: eivects[0] of the Hessian
-                                 want_tensor ? hessian_tensor.aaaafI : nullptr);
+                                 want_tensor ? hessian_tensor.aaaafI : nullptr,
+                                 subtract_background ? settings.width_b[0] : 0.0f,   // -membrane-background
+                                 settings.normalize_near_boundaries);
   }
   else
 #endif
@@ -95,8 +94,14 @@ def patch_handlers(t):
     t = edit(t, "  ApplyLog(tomo_in.header.nvoxels,", "  VISFD_NS::ApplyLog(tomo_in.header.nvoxels,", what="HandleLoGDoG")
     # ---- HandleTV ----
     tv = "HandleTV(const Settings &settings,"
-    t = edit(t, "  bool subtract_background = (settings.width_b[0] > 0.0);\n",
-             "  bool subtract_background = (settings.width_b[0] > 0.0);\n  bool visfd_fused = false;\n", after=tv, what="flag")
+    t = edit(t, "  bool subtract_background = (settings.width_b[0] > 0.0);\n  if (subtract_background) {\n",
+             "  bool subtract_background = (settings.width_b[0] > 0.0);\n  bool visfd_fused = false;\n"
+             "#ifdef VISFD_USE_CUDA\n"
+             "  visfd_fused = (settings.load_intermediate_fname_base == \"\") &&\n"
+             "                (settings.filter_type == Settings::SURFACE_RIDGE);\n"
+             "#endif\n"
+             "  if (subtract_background && (! visfd_fused)) {   // fused: the peak height is applied on the GPU\n",
+             after=tv, what="flag")
     t = edit(t, "  CalcHessian(image_size,", FUSED, after=tv, what="fused call")
     t = edit(t, "  for(int iz=0; iz < image_size[2]; iz++)\n    for(int iy=0; iy < image_size[1]; iy++)\n"
                 "      for(int ix=0; ix < image_size[0]; ix++)\n        tomo_out.aaafI[iz][iy][ix] = 0.0;\n",

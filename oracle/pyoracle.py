@@ -204,13 +204,22 @@ class Oracle:
         return res
 
     def membrane(self, src, sigma, truncate_ratio, order, cut, cut_is_fraction, tv_sigma,
-                 tv_exponent, tv_cutoff_ratio, mask=None, want_tensor=True):
+                 tv_exponent, tv_cutoff_ratio, mask=None, want_tensor=True, background_sigma=0.0, normalize=True):
         src = _f32(src)
         mask = _f32(mask)
         sal = np.zeros(src.shape, np.float32)
         dire = np.zeros(src.shape + (3,), np.float32)
         tensor = np.zeros(src.shape + (6,), np.float32) if want_tensor else None
         out = np.zeros(src.shape, np.float32)
+        if background_sigma > 0.0:      # `-membrane-background` (handlers.cpp:1577-1592); restatement only
+            if self.kind != "port":
+                raise RuntimeError("membrane with background subtraction: only the restatement has this entry")
+            thr = self._fn("membrane_background", _f)(*self._dims(src.shape), _ptr(src), _ptr(mask), _f(sigma),
+                                                      _f(truncate_ratio), _i(order), _f(cut), _i(int(cut_is_fraction)),
+                                                      _f(tv_sigma), _i(tv_exponent), _f(tv_cutoff_ratio),
+                                                      _f(background_sigma), _i(int(normalize)), _ptr(sal), _ptr(dire),
+                                                      _ptr(tensor), _ptr(out))
+            return dict(threshold=thr, hess_saliency=sal, direction=dire, tensor=tensor, out=out)
         thr = self._fn("membrane", _f)(*self._dims(src.shape), _ptr(src), _ptr(mask), _f(sigma),
                                        _f(truncate_ratio), _i(order), _f(cut),
                                        _i(int(cut_is_fraction)), _f(tv_sigma), _i(tv_exponent),

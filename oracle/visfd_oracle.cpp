@@ -726,18 +726,34 @@ void vo_tensor_score(i64 N, const float *tensor, const float *mask, int order,
 
 // Whole membrane path of HandleTV (bin/filter_mrc/handlers.cpp:1618-1892, no
 // background subtraction).  Optional outputs may be NULL.  Returns threshold.
-float vo_membrane(i64 nx, i64 ny, i64 nz, const float *src, const float *mask,
-                  float sigma, float truncate_ratio, int order, float cut,
-                  int cut_is_fraction, float tv_sigma, int tv_exponent,
-                  float tv_cutoff_ratio, float *hess_sal_out, float *dir_out,
-                  float *tensor_out, float *out) {
+float vo_membrane_background(i64 nx, i64 ny, i64 nz, const float *src, const float *mask,
+                             float sigma, float truncate_ratio, int order, float cut,
+                             int cut_is_fraction, float tv_sigma, int tv_exponent,
+                             float tv_cutoff_ratio, float background_sigma, int normalize,
+                             float *hess_sal_out, float *dir_out, float *tensor_out, float *out) {
   i64 N = nx * ny * nz;
   std::vector<float> grad(N * 3, 0.0f), hess(N * 6, 0.0f), sal(N, 0.0f);
+  // handlers.cpp:1577-1592 (`-membrane-background`): peak_height = tomo_in - Gauss(tomo_in, width_b) multiplies the
+  // ridge score (:1698-1702) and the post-vote score (:1883-1887).  (The second blur of that block, into tomo_out,
+  // is overwritten before anyone reads it.)
+  std::vector<float> peak;
+  if (background_sigma > 0.0f) {
+    std::vector<float> bg(src, src + N);               // tomo_background = tomo_in: masked voxels keep the source
+    float sg[3] = {background_sigma, background_sigma, background_sigma};
+    int h = (int)std::floor(background_sigma * truncate_ratio);
+    int hw[3] = {h, h, h};
+    vo_apply_gauss(nx, ny, nz, src, bg.data(), mask, sg, hw, normalize);
+    peak.resize(N);
+    for (i64 i = 0; i < N; i++) peak[i] = src[i] - bg[i];
+  }
   vo_calc_hessian(nx, ny, nz, src, mask, sigma, truncate_ratio, grad.data(),
                   hess.data(), nullptr);
   std::vector<float> dir(grad); // direction aliases gradient storage (:1633)
   vo_hessian_eigen_score(N, hess.data(), mask, order, 0, sal.data(), dir.data(),
                          nullptr);
+  if (!peak.empty())
+    for (i64 i = 0; i < N; i++)
+      if (!(mask && mask[i] == 0.0f)) sal[i] *= peak[i];
   float thr = vo_saliency_cut(N, sal.data(), mask, cut, cut_is_fraction);
   if (hess_sal_out) memcpy(hess_sal_out, sal.data(), N * sizeof(float));
   if (dir_out) memcpy(dir_out, dir.data(), 3 * N * sizeof(float));
@@ -747,9 +763,21 @@ float vo_membrane(i64 nx, i64 ny, i64 nz, const float *src, const float *mask,
     vo_tv_dense_stick(nx, ny, nz, sal.data(), dir.data(), mask, mask, tv_sigma,
                       tv_exponent, tv_cutoff_ratio, 0, tensor.data());
     vo_tensor_score(N, tensor.data(), mask, order, 0, out);
+    if (!peak.empty())
+      for (i64 i = 0; i < N; i++)
+        if (!(mask && mask[i] == 0.0f)) out[i] *= peak[i];
     if (tensor_out) memcpy(tensor_out, tensor.data(), 6 * N * sizeof(float));
   }
   return thr;
+}
+
+float vo_membrane(i64 nx, i64 ny, i64 nz, const float *src, const float *mask,
+                  float sigma, float truncate_ratio, int order, float cut,
+                  int cut_is_fraction, float tv_sigma, int tv_exponent,
+                  float tv_cutoff_ratio, float *hess_sal_out, float *dir_out,
+                  float *tensor_out, float *out) {
+  return vo_membrane_background(nx, ny, nz, src, mask, sigma, truncate_ratio, order, cut, cut_is_fraction, tv_sigma,
+                                tv_exponent, tv_cutoff_ratio, 0.0f, 1, hess_sal_out, dir_out, tensor_out, out);
 }
 
 // ---------------------------------------------------------------------------

@@ -3,7 +3,8 @@ STOCK filter_mrc binary (oracle/_ref/filter_mrc, compiled from /root/reference b
   c1_ply     the 58 vertices of the reference's own test, tests/test_membrane_detection.sh:9 (BASELINE config 1)
   s_*        a 40x44x48 synthetic tomogram (visfd_b200.synth, seed 3): `-membrane minima 3.4641 -tv 2.5
              -tv-angle-exponent 4 -bin 1 -connect T -connect-angle 30 -select-cluster 1 -normals-file`:
-             the volume, the cluster image the binary wrote, T and the PLY rows.
+             the volume, the cluster image the binary wrote, T and the PLY rows;
+  s_background6_out  the same volume through `-membrane ... -membrane-background 6` (no clustering): the output image.
 Run in the development container (needs /root/reference); the output travels as tests/golden/surface_points.npz."""
 import os
 import subprocess
@@ -58,6 +59,10 @@ def main():
         subprocess.run(base + ["-out", os.path.join(td, "p2.rec"), "-connect", repr(thr), "-connect-angle", "30",
                                "-select-cluster", "1", "-normals-file", os.path.join(td, "s.ply")], check=True,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        # `-membrane-background 6` (handlers.cpp:1577-1592): both scores times (source - blurred source)
+        subprocess.run(base + ["-out", os.path.join(td, "pb.rec"), "-membrane-background", "6"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _, out["s_background6_out"] = io.read(os.path.join(td, "pb.rec"))
         _, lab = io.read(os.path.join(td, "p2.rec"))
         out["s_vol"] = vol
         out["s_labels"] = lab.astype(np.uint8)

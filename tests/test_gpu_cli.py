@@ -118,3 +118,16 @@ def test_gauss_dog_through_the_cuda_cli(exe, golden, oracle, tmp_path):
     ga, _ = oracle.apply_gauss(vol, 1.5, hwa)
     gb, _ = oracle.apply_gauss(vol, 3.0, hwb)
     assert np.array_equal(d, ga - gb)
+
+
+def test_membrane_background_through_the_cuda_cli(exe, tmp_path):
+    """`-membrane-background` no longer leaves the fused GPU path (handlers.cpp:1577-1592): the stock binary's image"""
+    sp = np.load(os.path.join(ROOT, "tests", "golden", "surface_points.npz"))
+    io = mrc.open_library()
+    write_rec(io, tmp_path / "vol.rec", sp["s_vol"])
+    log = run([exe, "-w", "1", "-in", "vol.rec", "-out", "bg.rec", "-membrane", "minima", "3.4641", "-tv", "2.5",
+               "-tv-angle-exponent", "4", "-bin", "1", "-membrane-background", "6"], tmp_path)
+    assert "membrane pipeline on the GPU" in log
+    _, out = io.read(tmp_path / "bg.rec")
+    want = sp["s_background6_out"]
+    assert np.abs(out - want).max() <= 2e-4 * np.abs(want).max()

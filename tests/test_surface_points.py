@@ -130,3 +130,34 @@ def test_gpu_chain_from_the_raw_volume(ctx, sp_golden):
         den = np.maximum(np.abs(want), 1e-3 * np.abs(want).max(axis=0))
         bad = (np.abs(got.astype(np.float64) - want) / den).max(axis=1) > 1e-3
         assert bad.mean() <= 0.01, bad.mean()
+
+
+# ---- `-membrane-background` (handlers.cpp:1577-1592): lives here because the stock binary's answer for it was
+# made on the same synthetic volume ------------------------------------------------------------------------------
+def test_restatement_background_subtraction_is_the_stock_binary(oracle, sp_golden):
+    sigma, ratio, tv_sigma = synthetic_params()
+    m = oracle.membrane(sp_golden["s_vol"], sigma, ratio, 1, 0.05, True, tv_sigma, 4, SQ2, background_sigma=6.0)
+    assert np.array_equal(m["out"], sp_golden["s_background6_out"])
+
+
+@pytest.mark.gpu
+def test_gpu_background_subtraction(ctx, oracle, sp_golden):
+    from util import vote_score_err, rel_err, TOL_SALIENCY
+    sigma, ratio, tv_sigma = synthetic_params()
+    vol = sp_golden["s_vol"]
+    want = oracle.membrane(vol, sigma, ratio, 1, 0.05, True, tv_sigma, 4, SQ2, background_sigma=6.0, want_tensor=True)
+    got = ctx.membrane(vol, sigma, ratio, 1, 0.05, True, tv_sigma, 4, SQ2, background_sigma=6.0, want_saliency=True)
+    assert got["threshold"] == want["threshold"] or abs(got["threshold"] - want["threshold"]) <= 1e-5 * abs(want["threshold"])
+    assert rel_err(got["hess_saliency"], want["hess_saliency"]) <= TOL_SALIENCY
+    # the post-vote score times the peak height: judged like the score itself, against the tensor's trace times |peak|
+    peak = np.abs(sp_golden["s_background6_out"]).max()
+    assert np.abs(got["out"] - sp_golden["s_background6_out"]).max() <= 2e-4 * peak
+    # no voting, masked, device arrays
+    mask = np.ones_like(vol)
+    mask[:, :10, :] = 0
+    want = oracle.membrane(vol, sigma, ratio, 1, 0.05, True, 0.0, 4, SQ2, mask=mask, background_sigma=4.0)
+    import torch
+    got = ctx.membrane(torch.from_numpy(vol).cuda(), sigma, ratio, 1, 0.05, True, 0.0, 4, SQ2,
+                       mask=torch.from_numpy(mask).cuda(), background_sigma=4.0)
+    assert rel_err(got["out"].cpu().numpy(), want["out"]) <= TOL_SALIENCY
+    assert np.all(got["out"].cpu().numpy()[mask == 0] == 0)

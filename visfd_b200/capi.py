@@ -461,8 +461,9 @@ class Context:
 
     def membrane(self, src, sigma, truncate_ratio, order, cut, cut_is_fraction, tv_sigma, tv_exponent,
                  tv_cutoff_ratio, mask=None, want_saliency=False, want_direction=False, want_tensor=False,
-                 out=None):
-        """The fused HandleTV pipeline (bin/filter_mrc/handlers.cpp:1618-1892)."""
+                 out=None, background_sigma=0.0, normalize=True):
+        """The fused HandleTV pipeline (bin/filter_mrc/handlers.cpp:1618-1892); background_sigma > 0:
+        `-membrane-background` (:1577-1592)."""
         src, mask = _prep(src), _prep(mask)
         p = MembraneParams(sigma, truncate_ratio, order, cut, int(cut_is_fraction), tv_sigma, tv_exponent,
                            tv_cutoff_ratio)
@@ -471,8 +472,13 @@ class Context:
         dire = _zeros(src, tuple(src.shape) + (3,)) if want_direction else None
         tensor = _empty(src, tuple(src.shape) + (6,)) if want_tensor else None
         thr = _f()
-        self._ck(self.lib.visfd_cuda_membrane(self.h, *self._dims(src.shape), _ptr(src), _ptr(mask), C.byref(p),
-                                              _ptr(res), _ptr(sal), _ptr(dire), _ptr(tensor), C.byref(thr)))
+        if background_sigma > 0.0:
+            self._ck(self.lib.visfd_cuda_membrane_background(self.h, *self._dims(src.shape), _ptr(src), _ptr(mask),
+                                                             C.byref(p), _f(background_sigma), _i(int(normalize)),
+                                                             _ptr(res), _ptr(sal), _ptr(dire), _ptr(tensor), C.byref(thr)))
+        else:
+            self._ck(self.lib.visfd_cuda_membrane(self.h, *self._dims(src.shape), _ptr(src), _ptr(mask), C.byref(p),
+                                                  _ptr(res), _ptr(sal), _ptr(dire), _ptr(tensor), C.byref(thr)))
         return dict(out=res, hess_saliency=sal, direction=dire, tensor=tensor, threshold=thr.value)
 
     # ---- slab stages (device tensors only) -----------------------------------------------------------------

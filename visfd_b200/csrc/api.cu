@@ -335,14 +335,16 @@ static bool upload_smooth_ridge_chunked(visfd_ctx *ctx, int64_t nx, int64_t ny, 
   return true;
 }
 
-int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src,
-                        const float *mask, const visfd_membrane_params *p, float *out,
-                        float *hess_saliency, float *direction, float *tensor, float *threshold_out) {
-  API_BEGIN(ctx)
+// background_sigma > 0: `-membrane-background` (handlers.cpp:1577-1592): both scores are multiplied by
+// peak_height = source - Gauss(source, background_sigma) (:1698-1702, :1883-1887)
+static void membrane_impl(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src, const float *mask,
+                          const visfd_membrane_params *p, float background_sigma, int normalize, float *out,
+                          float *hess_saliency, float *direction, float *tensor, float *threshold_out) {
   check_dims(nx, ny, nz);
   VREQUIRE(src && p && out, "NULL argument");
   const size_t N = (size_t)nx * ny * nz;
   const bool host = on_host(src);
+  const bool peak = background_sigma > 0.0f;
   Staged<float> m(ctx, mask, N, Dir::In, host);
   Staged<float> o(ctx, out, N, Dir::Out, host);
   Staged<float> hs(ctx, hess_saliency, N, Dir::Out, host);
@@ -357,13 +359,27 @@ int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, cons
   if (!vote) sal = o.get();
   else if (hs.get()) sal = hs.get();
   else { sal_scratch.reset(ctx, N); sal = sal_scratch.get(); }
-  if (!(host && !mask && upload_smooth_ridge_chunked(ctx, nx, ny, nz, src, p, sm.get(), sal, dir.get()))) {
-    Staged<float> s(ctx, src, N, Dir::In, host);
-    smooth_for_hessian(ctx, nx, ny, nz, 0, nz, s.get(), m.get(), p->sigma, p->truncate_ratio, sm.get());
+  Staged<float> s_all;          // the whole source on the device: only when the peak height needs it
+  Scratch<float> bg;
+  if (peak) {
+    s_all.init(ctx, const_cast<float *>(src), N, Dir::In, host);
+    bg.reset(ctx, N);
+    const float sg[3] = {background_sigma, background_sigma, background_sigma};
+    const int h = (int)floorf(background_sigma * p->truncate_ratio);   // handlers.cpp:1582-1583
+    const int hw[3] = {h, h, h};
+    // tomo_background = tomo_in (:1580), then the blur: voxels outside the mask are never read back
+    gauss_device(ctx, nx, ny, nz, 0, nz, s_all.get(), bg.get(), m.get(), sg, hw, normalize != 0, nullptr, 1.0f);
+  }
+  if (peak || !(host && !mask && upload_smooth_ridge_chunked(ctx, nx, ny, nz, src, p, sm.get(), sal, dir.get()))) {
+    Staged<float> s_tmp;
+    if (!peak) s_tmp.init(ctx, const_cast<float *>(src), N, Dir::In, host);
+    const float *s = peak ? s_all.get() : s_tmp.get();
+    smooth_for_hessian(ctx, nx, ny, nz, 0, nz, s, m.get(), p->sigma, p->truncate_ratio, sm.get());
     ridge_device(ctx, nx, ny, nz, 0, nz, 0, nz, sm.get(), m.get(), p->sigma, p->eival_order,
                  VISFD_SCORE_PLANAR, sal, dir.get());
     // (the pool is stream-ordered: the staged source may be recycled once the work above is queued)
   }
+  if (peak) scale_by_peak_device(ctx, (i64)N, sal, s_all.get(), bg.get(), m.get());
   float thr = p->cut;
   if (p->cut_is_fraction) thr = select_threshold_device(ctx, N, sal, m.get(), p->cut);
   if (threshold_out) *threshold_out = thr;
@@ -371,9 +387,11 @@ int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, cons
     TVParams tp{p->tv_sigma, p->tv_exponent, p->tv_cutoff_ratio, 0};
     // voters' directions: the stored field if the caller asked for it, else recomputed
     // for the surviving ~5 % only
-    // with a host `out` the result travels back chunk by chunk behind the voting kernels
+    // with a host `out` the result travels back chunk by chunk behind the voting kernels (not when the peak height
+    // still has to multiply it)
     o.delivered = tv_device(ctx, nx, ny, nz, 0, nz, 0, nz, sal, thr, dir.get(), sm.get(), p->sigma, p->eival_order,
-                            VISFD_SCORE_PLANAR, m.get(), m.get(), tp, tn.get(), o.get(), host ? out : nullptr);
+                            VISFD_SCORE_PLANAR, m.get(), m.get(), tp, tn.get(), o.get(), (host && !peak) ? out : nullptr);
+    if (peak) scale_by_peak_device(ctx, (i64)N, o.get(), s_all.get(), bg.get(), m.get());
     if (hs.get()) apply_cut_device(ctx, N, hs.get(), thr);
   } else {
     apply_cut_device(ctx, N, sal, thr);
@@ -384,6 +402,24 @@ int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, cons
   hs.finish();
   dir.finish();
   tn.finish();
+}
+
+int visfd_cuda_membrane(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src,
+                        const float *mask, const visfd_membrane_params *p, float *out,
+                        float *hess_saliency, float *direction, float *tensor, float *threshold_out) {
+  API_BEGIN(ctx)
+  membrane_impl(ctx, nx, ny, nz, src, mask, p, 0.0f, 1, out, hess_saliency, direction, tensor, threshold_out);
+  API_END(ctx)
+}
+
+int visfd_cuda_membrane_background(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, const float *src,
+                                   const float *mask, const visfd_membrane_params *p, float background_sigma,
+                                   int normalize_near_boundaries, float *out, float *hess_saliency, float *direction,
+                                   float *tensor, float *threshold_out) {
+  API_BEGIN(ctx)
+  VREQUIRE(background_sigma >= 0.0f, "negative background width");
+  membrane_impl(ctx, nx, ny, nz, src, mask, p, background_sigma, normalize_near_boundaries, out, hess_saliency, direction,
+                tensor, threshold_out);
   API_END(ctx)
 }
 

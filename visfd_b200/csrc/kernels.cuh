@@ -52,6 +52,7 @@ i64 count_unmasked_device(visfd_ctx *ctx, i64 n, const float *mask);
 float select_threshold_device(visfd_ctx *ctx, i64 n, const float *sal, const float *mask,
                               float fraction);
 void apply_cut_device(visfd_ctx *ctx, i64 n, float *sal, float thr);
+void scale_by_peak_device(visfd_ctx *ctx, i64 n, float *score, const float *src, const float *background, const float *mask);
 
 // ---- tv.cu ------------------------------------------------------------------------
 struct TVParams {

@@ -192,6 +192,27 @@ void apply_cut_device(visfd_ctx *ctx, i64 n, float *sal, float thr) {
   ctx->count_launch();
 }
 
+// peak_height of `-membrane-background` (handlers.cpp:1698-1702, :1883-1887): score *= source - background, for the
+// voxels the reference visits (mask != 0)
+__global__ void scale_by_peak_kernel(float *__restrict__ score, const float *__restrict__ src, const float *__restrict__ bg,
+                                     const float *__restrict__ mask, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    if (mask && __ldg(mask + i) == 0.0f) continue;
+    score[i] = __fmul_rn(score[i], __fsub_rn(__ldg(src + i), __ldg(bg + i)));
+  }
+}
+
+void scale_by_peak_device(visfd_ctx *ctx, i64 n, float *score, const float *src, const float *background, const float *mask) {
+  if (n == 0) return;
+  StageTimer t(ctx, "ridge");
+  int grid = (int)std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16);
+  scale_by_peak_kernel<<<grid, 256, 0, ctx->stream>>>(score, src, background, mask, n);
+  VCK(cudaGetLastError());
+  ctx->count_launch();
+}
+
 __global__ void count_unmasked_kernel(const float *__restrict__ mask, i64 n, unsigned long long *out) {
   i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   i64 stride = (i64)gridDim.x * blockDim.x;

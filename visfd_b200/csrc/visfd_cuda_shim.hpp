@@ -447,13 +447,15 @@ class TV3D {
 inline float MembranePipeline(int const image_size[3], float const *const *const *aaafSource, float ***aaafDest,
                               float const *const *const *aaafMask, const visfd_membrane_params &p,
                               std::array<float, 3> ***aaaafDirection = nullptr,
-                              float ****aaaafVoteTensor = nullptr) {
+                              float ****aaaafVoteTensor = nullptr, float background_sigma = 0.0f /* settings.width_b[0] */,
+                              bool normalize_near_boundaries = true) {
   Dense3<float, 1> s(image_size, aaafSource, false), m(image_size, aaafMask, false), d(image_size, aaafDest, true);
   Dense3<std::array<float, 3>, 3> dir(image_size, aaaafDirection, true);
   DenseTensor t(image_size, aaaafVoteTensor, 6, false);
   float thr = 0;
-  Check(visfd_cuda_membrane(Context(), image_size[0], image_size[1], image_size[2], s.data(), m.data(), &p, d.data(),
-                            nullptr, dir.data(), t.data(), &thr));
+  Check(visfd_cuda_membrane_background(Context(), image_size[0], image_size[1], image_size[2], s.data(), m.data(), &p,
+                                       background_sigma > 0.0f ? background_sigma : 0.0f, normalize_near_boundaries ? 1 : 0,
+                                       d.data(), nullptr, dir.data(), t.data(), &thr));
   d.commit();
   dir.commit();
   t.commit();
