@@ -4,9 +4,9 @@
 // The reference visits all (2hw+1)^3 offsets of every receiver and skips the ~95 % of
 // them whose voter has zero saliency.  Here the voters (saliency != 0 after the cut,
 // mask != 0) are first compacted into a list ordered by 4x4x4 BRICK (count -> exclusive
-// scan -> fill -> direction: streaming passes over the saliency volume, made by kernels that
-// work on 8x8x8 regions), 48 B per voter, laid out as the voting kernels consume them
-// (struct VoterRec).  The gather runs one WARP per 4x4x4 receiver patch (lane = (x, y, half);
+// scan -> fill -> direction: two row-streaming passes over the saliency volume, a warp per
+// run of 8 bricks, and one thread per voter for its normal), 48 B per voter, laid out as the
+// voting kernels consume them (struct VoterRec).  The gather runs one WARP per 4x4x4 receiver patch (lane = (x, y, half);
 // four z-receivers per lane; the two half-warps take different voters): it builds the table of
 // brick rows that can reach the patch, streams their voters through an exact voter-to-patch
 // distance test into a warp-private cp.async ring in shared memory, and drains the ring 32
@@ -18,7 +18,9 @@
 //                             the INTEGER r^2 (positions are lattice points), 16 replicas so that
 //                             the lanes of a half-warp never share a bank.  Exponent 4, positive
 //                             weights, vote radius <= 24: the filter_mrc default and BASELINE's
-//                             configurations.  No MUFU, no support mask in the loop.
+//                             configurations.  No MUFU, no support mask, no address arithmetic in
+//                             the loop: the r^2 accumulator is a DENORMAL float whose bit pattern is
+//                             the shared-memory address of the table row (see LUT_* below).
 // The reference's decay TABLE (lib/visfd/filter3d.hpp:546-601) is only needed for two things,
 // both computed on the host with the reference's own float expressions: the normalisation
 // constant (sum over the cube) and which lattice points on the shell r^2 == hw^2 survive the
@@ -26,7 +28,7 @@
 //
 // Epilogue (fused, accumulators still in registers): optional store of the 6-component
 // tensor (-save-progress) and DiagonalizeFlatSym3 + ScoreTensorPlanar/Linear
-// (bin/filter_mrc/handlers.cpp:1870-1892) in double.
+// (bin/filter_mrc/handlers.cpp:1870-1892), eigenvalues in double (eigen3.cuh: sym3_eigenvalues_newton).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -854,7 +856,10 @@ __global__ void __launch_bounds__(TV_THREADS, TV_MIN_CTAS) tv_gather_kernel(Gath
 // same time and find each other's candidates in L1, and a warp that finishes early takes the first patch of the
 // quad's next tile instead of idling.  The warp that draws a tile's first ticket fetches the tile number from the
 // device-wide counter and publishes it in shared memory; the other three pick it up there.
-constexpr int LUT_WARPS = 16, LUT_QUADS = LUT_WARPS / 4, LUT_SEQ = 8;   // a slot is reused 32 tickets later
+#ifndef LUT_WARPS_N
+#define LUT_WARPS_N 16
+#endif
+constexpr int LUT_WARPS = LUT_WARPS_N, LUT_QUADS = LUT_WARPS / 4, LUT_SEQ = 8;   // a slot is reused 32 tickets later
 template <bool CURVES, bool CLAMP>
 __global__ void __launch_bounds__(32 * LUT_WARPS, 1) tv_gather_lut_kernel(GatherArgs g) {
   extern __shared__ __align__(16) unsigned char tv_smem[];
