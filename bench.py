@@ -48,11 +48,14 @@ TV_BEST = 0.05
 WORKLOADS = {"C4": (1024, 2048, 2048), "C5": (1024, 4096, 4096), "C2": (512, 512, 512), "C3": (512, 1024, 1024),
              "dev": (256, 256, 256)}
 CPU_SAMPLE = tuple(int(v) for v in os.environ.get("VISFD_BENCH_CPU_SAMPLE", "128,128,128").split(","))  # override: smoke tests
-# dram__bytes_read.sum + dram__bytes_write.sum of one tv_gather_kernel launch, from the
-# `ncu --set full` capture of the named workload (profiles/r01_tv_gather_ncu_full.csv)
-# ("C4": a metrics-only ncu pass of `bench.py --steps 1 --warmup 0`: the 10.3 GB voter list is
-# re-read once per layer of receiver tiles it serves; 10.7 GB/s, nowhere near the HBM roofline)
-NCU_TRAFFIC_BYTES = {"dev": 42.21e6 + 21.52e6, "C4": 72.06e9 + 17.45e9}
+# dram__bytes_read.sum + dram__bytes_write.sum of the voting kernel, per pipeline pass, from an ncu capture of
+# the named workload -- constants of a PROFILED run of the same command, not measured in this run (a number taken
+# under a profiler is never a bench value; the traffic of a kernel is).
+#   dev: profiles/r02_tv_gather_lut_ncu_full.csv (ncu --set full, tv_gather_lut_kernel, 256^3)
+#   C4:  profiles/r02_tv_traffic_c4.csv (ncu --replay-mode application, `bench.py --steps 1 --warmup 0`): the 10.3 GB
+#        voter list is re-read ~11 times from DRAM by the layers of receiver tiles it serves (L2 hit rate 99 %);
+#        20 GB/s, nowhere near the HBM roofline
+NCU_TRAFFIC_BYTES = {"dev": 41.90e6 + 21.66e6, "C4": 115.59e9 + 17.30e9}
 
 
 def parse():
@@ -239,11 +242,15 @@ def workload_config(name, shape):
             "l2": "inputs (>= 0.5 GB per volume) exceed the 126 MB L2; no flush needed"}
 
 
-def gauss_c2_table(ctx, dev, hbm_peak):
+def gauss_c2_table(ctx, dev, hbm_peak, fp32_peak):
     """ApplyGauss and ApplyDog (sigma, 1.6 sigma) on a synthetic 512^3 volume for sigma 2, 4, 8
     (half-widths 5, 10, 21), device resident, CUDA events, 5 launches after 2
     warm-ups.  Algorithmic bytes: 24 B/voxel per Gaussian, 48 per DoG.  `exact` is the
-    default bit-identical arithmetic (un-fused multiply and add per tap), `fast` the FFMA mode."""
+    default bit-identical arithmetic (un-fused multiply and add per tap), `fast` the FFMA mode.
+    Beyond sigma ~ 3 the direct convolution is FP32-bound, so every row also carries the fraction of the FMA
+    pipe: (2 hw + 1) taps x 3 sweeps x (2 pipe operations per tap in the exact mode -- a multiply and an add, the
+    reference's rounding sequence -- 1 in the FFMA mode) per voxel, against the lane rate behind the FP32 peak
+    measured in this run (peak TFLOP/s / 2 FLOP per FMA); `bound` names the larger of the two."""
     import torch
     import visfd_b200
     from visfd_b200 import synth
@@ -271,10 +278,17 @@ def gauss_c2_table(ctx, dev, hbm_peak):
             hw_dog = visfd_b200.gauss_halfwidth(1.6 * sigma)
             ms_g = timed_ms(lambda: ctx.apply_gauss(vol, [sigma] * 3, [hw] * 3))
             ms_d = timed_ms(lambda: ctx.apply_dog(vol, [sigma] * 3, [1.6 * sigma] * 3, [hw_dog] * 3))
+            ops = 2.0 if mode == "exact" else 1.0
+            lane_rate = fp32_peak * 1e12 / 2.0
+            g_pipe = n * (2 * hw + 1) * 3 * ops / (ms_g * 1e-3) / lane_rate
+            d_pipe = n * (2 * hw_dog + 1) * 3 * 2 * ops / (ms_d * 1e-3) / lane_rate
+            g_hbm, d_hbm = 24.0 * n / ms_g / 1e6 / hbm_peak, 48.0 * n / ms_d / 1e6 / hbm_peak
             rows.append({"mode": mode, "sigma": sigma, "halfwidth": hw, "gauss_ms": ms_g,
-                         "gauss_GBps": 24.0 * n / ms_g / 1e6, "gauss_frac_of_hbm": 24.0 * n / ms_g / 1e6 / hbm_peak,
+                         "gauss_GBps": 24.0 * n / ms_g / 1e6, "gauss_frac_of_hbm": g_hbm,
+                         "gauss_frac_of_fp32_pipe": g_pipe, "gauss_bound": "fp32" if g_pipe > g_hbm else "hbm",
                          "dog_halfwidth": hw_dog, "dog_ms": ms_d, "dog_GBps": 48.0 * n / ms_d / 1e6,
-                         "dog_frac_of_hbm": 48.0 * n / ms_d / 1e6 / hbm_peak})
+                         "dog_frac_of_hbm": d_hbm, "dog_frac_of_fp32_pipe": d_pipe,
+                         "dog_bound": "fp32" if d_pipe > d_hbm else "hbm"})
     ctx.set_fast_gauss(False)
     del vol
     torch.cuda.empty_cache()
@@ -655,11 +669,18 @@ def main():
              "unit": "GB/s", "algorithmic_bytes_per_voxel": 8, "kernel_ms": stage["ridge"]}
     ridge["frac"] = ridge["achieved"] / hbm_peak
     ridge["frac_of_nominal_8000_GBps"] = ridge["achieved"] / 8000.0
+    # SURVEY 8d counts 20 B/voxel for this pass (4 in, 4 saliency + 12 normal out); the fused pipeline never writes
+    # the normals (they are recomputed for the ~5 % of voxels that vote), hence 8.  The pass is bound by the FP64 /
+    # conversion pipes, not by HBM: ~58 DFMA-class instructions (64 per clock and SM), 8 float<->double conversions
+    # + 3 MUFU (16 per clock and SM) per voxel
+    ridge["frac_at_survey_20_bytes_per_voxel"] = 20.0 / 8.0 * ridge["frac"]
+    ridge["fp64_instructions_per_voxel"] = 58
+    ridge["frac_of_fp64_pipe"] = 58.0 * n_slab_vox / (stage["ridge"] * 1e-3) / (64.0 * 148 * 1.965e9)
 
     # ---- BASELINE config 2: 3-D Gaussian / DoG at sigma 2, 4, 8 on 512^3 (the "Gauss HBM GB/s" half) ---
     gauss_c2 = blob_c3 = None
     if rank == 0 and world == 1:
-        gauss_c2 = gauss_c2_table(ctx, dev, hbm_peak)
+        gauss_c2 = gauss_c2_table(ctx, dev, hbm_peak, fp32_peak)
         blob_c3 = blob_c3_row(ctx, dev, hbm_peak)
 
     # ---- end to end: host buffers through the public call ------------------------------------------

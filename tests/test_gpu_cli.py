@@ -131,3 +131,52 @@ def test_membrane_background_through_the_cuda_cli(exe, tmp_path):
     _, out = io.read(tmp_path / "bg.rec")
     want = sp["s_background6_out"]
     assert np.abs(out - want).max() <= 2e-4 * np.abs(want).max()
+
+
+def test_cli_filters_a_volume_beyond_2_31_voxels(exe, oracle, tmp_path):
+    """with Alloc3D's products in size_t and MrcSimple's named-file Read / Write going through
+    include/visfd_mrc.h (both edits of integration/build_filter_mrc_cuda.py), the reference's own program reads,
+    filters (`-gauss 2`, on the GPU) and writes a 1296 x 1296 x 1280 volume = 2.15e9 voxels > 2^31.  Checked against
+    the oracle on crops (bit for bit), including the planes that hold flat index 2^31 and the global z border."""
+    import shutil
+    import psutil
+    nz, ny, nx = 1280, 1296, 1296
+    n = nz * ny * nx
+    assert n > 2 ** 31
+    if shutil.disk_usage(tmp_path).free < 3 * 4 * n or psutil.virtual_memory().available < 6 * 4 * n:
+        pytest.skip("needs ~26 GB of scratch disk and ~52 GB of free host memory")
+    rng = np.random.default_rng(11)
+    tile = rng.standard_normal((16, ny, nx)).astype(np.float32)
+    hdr = mrc.MrcHeader()
+    hdr.nvoxels[:] = (nx, ny, nz)
+    hdr.mvoxels[:] = (nx, ny, nz)
+    hdr.mode = 2
+    hdr.cellA[:] = (float(nx), float(ny), float(nz))
+    hdr.cellB[:] = (90.0, 90.0, 90.0)
+    hdr.mapCRS[:] = (1, 2, 3)
+
+    def plane_block(z0, z1):
+        return np.stack([tile[z % 16] + np.float32(0.01 * z) for z in range(z0, z1)])
+
+    src = tmp_path / "big.rec"
+    with open(src, "wb") as f:
+        f.write(hdr.as_bytes()[:1024])     # (the struct carries one more field than the file header)
+        for z0 in range(0, nz, 16):
+            plane_block(z0, min(z0 + 16, nz)).tofile(f)
+    run([exe, "-w", "1", "-in", "big.rec", "-out", "big_gauss.rec", "-gauss", "2"], tmp_path)
+    out = np.memmap(tmp_path / "big_gauss.rec", dtype=np.float32, mode="r", offset=1024, shape=(nz, ny, nx))
+    assert os.path.getsize(tmp_path / "big_gauss.rec") == 1024 + 4 * n
+    hw = 5   # floor(2 * 2.6482)
+    z_of_2_31 = (2 ** 31) // (ny * nx)
+    for (za, zb, ya, yb, xa, xb) in ((600, 640, 100, 164, 1200, 1296),           # interior in z, the x border
+                                     (z_of_2_31 - 24, nz, 0, 48, 0, 64),          # flat index 2^31, the z and y borders
+                                     (0, 24, ny - 40, ny, 640, 700)):             # the first planes
+        # margin of hw towards the interior, the volume's own border otherwise (the oracle renormalises there too)
+        lo = [max(za - hw, 0), max(ya - hw, 0), max(xa - hw, 0)]
+        hi = [min(zb + hw, nz), min(yb + hw, ny), min(xb + hw, nx)]
+        crop = plane_block(lo[0], hi[0])[:, lo[1]:hi[1], lo[2]:hi[2]]
+        want, _ = oracle.apply_gauss(np.ascontiguousarray(crop), 2.0, hw)
+        sl = (slice(za - lo[0], zb - lo[0]), slice(ya - lo[1], yb - lo[1]), slice(xa - lo[2], xb - lo[2]))
+        got = np.asarray(out[za:zb, ya:yb, xa:xb])
+        assert np.array_equal(got, want[sl]), (za, ya, xa, float(np.abs(got - want[sl]).max()))
+    del out

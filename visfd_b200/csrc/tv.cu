@@ -124,12 +124,16 @@ struct VoterRows {
   float s[VL_ROWS];       // saliency * mask weight, or 0 where the voxel is no voter
   __device__ __forceinline__ void load(const VoterSrc &v, int x, int by, int bz) {
     float m[VL_ROWS];
+    // one base index and two strides instead of sixteen 64-bit index computations
+    const int ylim = v.ny - by * VBR;                 // rows (r & 3) < ylim exist
+    const i64 zlim = v.nz - (i64)bz * VBR;            // planes (r >> 2) < zlim exist
+    const i64 sy = v.nx, sz = (i64)v.nx * v.ny;
+    const i64 i0 = ((i64)bz * VBR * v.ny + (i64)by * VBR) * v.nx + x;
+    const bool xin = x < v.nx;
 #pragma unroll
     for (int r = 0; r < VL_ROWS; r++) {
-      const int y = by * VBR + (r & 3);
-      const i64 z = (i64)bz * VBR + (r >> 2);
-      const bool in = x < v.nx && y < v.ny && z < v.nz;
-      const i64 i = (z * v.ny + y) * (i64)v.nx + x;
+      const bool in = xin && (r & 3) < ylim && (r >> 2) < zlim;
+      const i64 i = i0 + (r & 3) * sy + (r >> 2) * sz;
       s[r] = in ? __ldg(v.sal + i) : 0.0f;
       m[r] = (in && v.mask_src) ? __ldg(v.mask_src + i) : 1.0f;
     }
@@ -324,21 +328,14 @@ voter_fill_kernel(VoterSrc v, const uint32_t *__restrict__ off, float inv_total,
     if (rows.s[r] != 0.0f) {
       const float wgt = rows.s[r] * inv_total;
       if (!(wgt > 0.0f)) *nonpos_flag = 1u;  // benign race: every writer stores the same value
-      // the three forms of the weight the gather kernels fold into their arithmetic (vote())
-      const float w4 = 4.0f * wgt, l4 = log2f(w4);
+      // position and raw weight only: the forms of the weight that the gather kernels fold into their arithmetic
+      // (a logarithm, a sixth root) are computed by voter_direction_kernel, where every lane has a voter -- here
+      // ~5 % of the lanes do, and a warp would run the libm sequence for them at that lane efficiency
       VoterRec *q = rec + base + rank + __popc(nib & below);
       const float px = -(float)x, py = -(float)(by * VBR + (r & 3)), pz = -(float)(bz * VBR + (r >> 2));
-      if (lut) {   // only used when every weight is positive (checked by the host before the launch)
-        const float lam = (float)pow((double)fmaxf(w4, 0.0f), 1.0 / 6.0);
-        const float rho = pow2f(LUT_RHO_LOG2);
-        q->a = make_float4(px * rho, py * rho, pz * rho, lam * lam * pow2f(LUT_K_LOG2));
-        q->b.w = lam;
-        q->c.w = 0.0f;
-      } else {
-        q->a = make_float4(px, py, pz, 0.5f * l4);
-        q->b.w = l4;
-        q->c.w = w4;
-      }
+      const float cs = lut ? pow2f(LUT_RHO_LOG2) : 1.0f;
+      q->a = make_float4(px * cs, py * cs, pz * cs, 0.0f);
+      q->c.w = 4.0f * wgt;
     }
     rank += __popc(nib);
   }
@@ -355,10 +352,19 @@ voter_direction_kernel(DirSrc d, int nx, int ny, uint32_t n_voters, bool lut, Vo
   if (lut) { const float un = pow2f(-LUT_RHO_LOG2); a.x *= un; a.y *= un; a.z *= un; }
   float n[3];
   voter_direction(d, nx, ny, (int)(-a.x), (int)(-a.y), (i64)(-a.z), n);
+  // the weight w4 = 4 * saliency * mask weight / table total in the three forms vote() / vote_lut() use
+  const float w4 = r->c.w;
   float sb = 1.0f, sc = 0.5f;
-  if (lut) {
-    const float lam = r->b.w;
+  if (lut) {   // only used when every weight is positive (checked by the host before the launch)
+    const float lam = (float)pow((double)fmaxf(w4, 0.0f), 1.0 / 6.0);
     sb = lam * pow2f(LUT_BETA_LOG2); sc = lam * pow2f(LUT_BETA2_LOG2);
+    r->a.w = lam * lam * pow2f(LUT_K_LOG2);
+    r->b.w = lam;
+    r->c.w = 0.0f;
+  } else {
+    const float l4 = log2f(w4);
+    r->a.w = 0.5f * l4;
+    r->b.w = l4;
   }
   r->b.x = sb * n[0]; r->b.y = sb * n[1]; r->b.z = sb * n[2];
   r->c.x = sc * n[0]; r->c.y = sc * n[1]; r->c.z = sc * n[2];
