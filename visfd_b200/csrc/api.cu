@@ -466,7 +466,7 @@ int visfd_cuda_vote_slab_host(visfd_ctx *ctx, int64_t nx, int64_t ny, int64_t nz
     VREQUIRE((vote_z0 >= 1 || z_offset == 0) && (vote_z1 <= nz_local - 1 || z_offset + nz_local == nz_global),
              "slab lacks the 1-plane halo around the voter planes");
     TVParams tp{p->tv_sigma, p->tv_exponent, p->tv_cutoff_ratio, 0};
-    // The voter list is ordered by brick (4^3, built from 8^3 regions) and float sums depend on the order, so the voter planes
+    // The voter list is ordered by 4^3 brick and float sums depend on the order, so the voter planes
     // start on a GLOBAL multiple of 8 whenever the slab has the planes for it (the extra ones are out of
     // every receiver's reach): with receiver planes that start on a multiple of 4 as well, a slab then
     // reproduces the undivided volume bit for bit.

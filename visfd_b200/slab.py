@@ -28,7 +28,7 @@ import numpy as np
 def partition(nz, world):
     """Contiguous, near-equal plane ranges [z0, z1) per rank.  When there are at least 8 planes per rank
     the boundaries are multiples of 8 (the last rank takes the ragged tail): the voting kernel's 4x4x4
-    receiver patches and the voter bricks (4^3, built from 8^3 regions) then fall where they fall in the undivided volume, which makes
+    receiver patches and the voter bricks (both 4^3; 8 planes = one layer of 8x8x4 receiver tiles twice over, a margin kept from the first voter-list kernels) then fall where they fall in the undivided volume, which makes
     the result independent of the number of ranks bit for bit."""
     unit = 8 if nz // 8 >= world else 1
     base, rem = divmod(nz // unit, world)
@@ -66,7 +66,7 @@ def make_plan(nz, world, rank, gauss_hw, tv_hw):
     halo = (tv_hw + 1 + gauss_hw) if tv_hw > 0 else (1 + gauss_hw)
 
     def widened(r, h):
-        # The slab starts on a multiple of 8 planes: the voting stage orders its voters by brick (4^3, built from 8^3 regions),
+        # The slab starts on a multiple of 8 planes: the voting stage orders its voters by 4^3 brick,
         # and with the slab's bricks coinciding with the whole volume's every receiver meets its
         # voters in the same order -- the multi-GPU result is then BIT-identical to the one-GPU one
         # (float sums depend on the order), at the price of up to 7 extra halo planes.
