@@ -246,6 +246,43 @@ def test_hessian_ridge(ctx, oracle, order):
     assert direction_err(dire, want_dir, weight=strong) <= 1e-4
 
 
+def test_ridge_march_kernel_edges(ctx, oracle):
+    """The saliency-only kernel (ridge_march_kernel: z-marching register windows) at the shapes where its plane
+    bookkeeping can go wrong: 3 planes (every plane uses the stencil of plane 1), chunks of 32 planes that end one
+    plane before / on / after the volume, both eigenvalue orders, the linear score, a mask, and slab-local plane
+    ranges with a global offset; against the kernel that writes normals too (one thread per voxel) and the oracle."""
+    rng = np.random.default_rng(21)
+    for shape in ((3, 3, 3), (3, 7, 5), (4, 9, 66), (31, 5, 6), (32, 4, 130), (33, 6, 7), (65, 5, 9)):
+        vol = rng.standard_normal(shape).astype(np.float32)
+        for order in (0, 1):
+            for kind in (vb.SCORE_PLANAR, vb.SCORE_LINEAR):
+                a, _ = ctx.hessian_ridge(vol, 1.2, 2.6482, order=order, score_kind=kind, want_direction=False)
+                b, _ = ctx.hessian_ridge(vol, 1.2, 2.6482, order=order, score_kind=kind, want_direction=True)
+                assert rel_err(a, b) <= 1e-5, (shape, order, kind)
+        g, h = oracle.calc_hessian(vol, 1.2, 2.6482)
+        want, _, _ = oracle.hessian_eigen_score(h, order=1)
+        got, _ = ctx.hessian_ridge(vol, 1.2, 2.6482, order=1, want_direction=False)
+        assert rel_err(got, want) <= TOL_SALIENCY, shape
+        mask = (rng.random(shape) > 0.3).astype(np.float32)
+        g, h = oracle.calc_hessian(vol, 1.2, 2.6482, mask=mask)
+        want, _, _ = oracle.hessian_eigen_score(h, order=1, mask=mask)
+        got, _ = ctx.hessian_ridge(vol, 1.2, 2.6482, order=1, mask=mask, want_direction=False)
+        assert rel_err(got, want) <= TOL_SALIENCY and np.all(got[mask == 0] == 0), shape
+    # slab stage: planes [z_offset, z_offset + n) of a taller volume; the planes next to an internal face are not
+    # produced (zero), every other plane equals the whole-volume result bit for bit
+    import torch
+    vol = rng.standard_normal((70, 12, 20)).astype(np.float32)
+    whole, _ = ctx.hessian_ridge(vol, 1.2, 2.6482, order=1, want_direction=False)
+    hw = 3   # floor(1.2 * 2.6482)
+    for (lo, hi) in ((0, 40), (17, 70), (20, 55), (33, 66)):
+        dev = torch.from_numpy(np.ascontiguousarray(vol[lo:hi])).cuda()
+        sm, sal = ctx.ridge_saliency_slab(dev, lo, vol.shape[0], 1.2, 2.6482, order=1)
+        sal = sal.cpu().numpy()
+        a = 0 if lo == 0 else hw + 1
+        b = hi - lo if hi == vol.shape[0] else hi - lo - hw - 1
+        assert np.array_equal(sal[a:b], whole[lo + a:lo + b]), (lo, hi)
+
+
 def test_hessian_ridge_masked(ctx, oracle):
     vol = synth.tomogram((30, 34, 40), seed=12)
     mask = np.ones(vol.shape, np.float32)
