@@ -625,6 +625,48 @@ __device__ __forceinline__ void drain(const VoterRec *q, int n, float fx, float 
     }
   }
 }
+// The two halves' tensors are added (half 0 finishes receivers z, z+1, half 1 z+2, z+3), then the optional
+// 6-component store and the post-vote score, accumulators still in registers.
+__device__ __forceinline__ void patch_epilogue(const GatherArgs &g, const float2 T[12], int half, int ix, int iy, int pz) {
+  float2 Tm[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const float2 give = half ? T[k] : T[k + 6];      // what the partner lane finishes
+    const float2 keep = half ? T[k + 6] : T[k];
+    Tm[k].x = keep.x + __shfl_xor_sync(0xffffffffu, give.x, 16);
+    Tm[k].y = keep.y + __shfl_xor_sync(0xffffffffu, give.y, 16);
+  }
+  const int iz = pz + 2 * half;
+  if (ix < g.nx && iy < g.ny) {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const i64 z = iz + r;
+      if (z >= g.own_z1) break;
+      float Tr[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) Tr[k] = r ? Tm[k].y : Tm[k].x;
+      const i64 slab_i = (z * g.ny + iy) * (i64)g.nx + ix;
+      const i64 out_i = ((z - g.own_z0) * g.ny + iy) * (i64)g.nx + ix;
+      const bool masked = g.mask_dst && __ldg(g.mask_dst + slab_i) == 0.0f;  // feature.hpp:2002-2003
+      if (g.tensor) {
+        float *o = g.tensor + 6 * out_i;
+#pragma unroll
+        for (int k = 0; k < 6; k++) o[k] = masked ? 0.0f : Tr[k];
+      }
+      if (g.score) {
+        float sc = 0.0f;
+        if (!masked) {
+          Sym3d mm = {Tr[0], Tr[1], Tr[2], Tr[3], Tr[4], Tr[5]};
+          double ev[3];
+          sym3_eigenvalues(mm, g.order, ev);
+          sc = score_from_eivals(ev, g.score_kind, 1);
+        }
+        g.score[out_i] = sc;
+      }
+    }
+  }
+}
+
 // One WARP per 4x4x4 receiver patch.  Lane = (x, y, h): the lanes of half-warp h hold all four
 // z-receivers of their (x, y) column (24 accumulators as twelve packed pairs), and the two
 // half-warps evaluate DIFFERENT voters in the same iteration -- h takes every second ring entry
@@ -802,46 +844,7 @@ __device__ __forceinline__ void gather_patch(const GatherArgs &g, const unsigned
     cnt -= n;
   }
 
-  // ---- the two halves' tensors: half 0 finishes receivers z, z+1, half 1 z+2, z+3 ---------
-  float2 Tm[6];
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    const float2 give = half ? T[k] : T[k + 6];      // what the partner lane finishes
-    const float2 keep = half ? T[k + 6] : T[k];
-    Tm[k].x = keep.x + __shfl_xor_sync(0xffffffffu, give.x, 16);
-    Tm[k].y = keep.y + __shfl_xor_sync(0xffffffffu, give.y, 16);
-  }
-  const int iz = pz + 2 * half;
-
-  // ---- epilogue ---------------------------------------------------------------------
-  if (ix < g.nx && iy < g.ny) {
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      const i64 z = iz + r;
-      if (z >= g.own_z1) break;
-      float Tr[6];
-#pragma unroll
-      for (int k = 0; k < 6; k++) Tr[k] = r ? Tm[k].y : Tm[k].x;
-      const i64 slab_i = (z * g.ny + iy) * (i64)g.nx + ix;
-      const i64 out_i = ((z - g.own_z0) * g.ny + iy) * (i64)g.nx + ix;
-      const bool masked = g.mask_dst && __ldg(g.mask_dst + slab_i) == 0.0f;  // feature.hpp:2002-2003
-      if (g.tensor) {
-        float *o = g.tensor + 6 * out_i;
-#pragma unroll
-        for (int k = 0; k < 6; k++) o[k] = masked ? 0.0f : Tr[k];
-      }
-      if (g.score) {
-        float sc = 0.0f;
-        if (!masked) {
-          Sym3d mm = {Tr[0], Tr[1], Tr[2], Tr[3], Tr[4], Tr[5]};
-          double ev[3];
-          sym3_eigenvalues(mm, g.order, ev);
-          sc = score_from_eivals(ev, g.score_kind, 1);
-        }
-        g.score[out_i] = sc;
-      }
-    }
-  }
+  patch_epilogue(g, T, half, ix, iy, pz);
 }
 
 
