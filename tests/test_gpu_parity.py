@@ -128,6 +128,28 @@ def test_dog_log(ctx, oracle):
     assert np.array_equal(got, want)
 
 
+def test_dog_shared_z_sweep_with_unequal_halfwidths(ctx, oracle):
+    """The pair of Gaussians of a DoG shares one Z sweep (the shorter filter zero-padded and centred in the
+    longer one's tap array) whenever that costs no extra group of 8 taps: half-widths 5 and 7 qualify, 5 and 12
+    take the separate sweeps.  Either way: the two oracle Gaussians, subtracted, bit for bit."""
+    vol = synth.tomogram((44, 36, 64), seed=12)
+    for hw_a, hw_b in ((5, 7), (7, 5), (5, 12), (0, 3)):
+        ga, _ = oracle.apply_gauss(vol, 2.0, hw_a)
+        gb, _ = oracle.apply_gauss(vol, 2.9, hw_b)
+        got, _, _ = ctx.apply_dog(vol, 2.0, 2.9, hw_a, hw_b=hw_b)
+        assert np.array_equal(got, ga - gb), (hw_a, hw_b)
+    # the FFMA mode shares the sweep up to one extra group of taps (5 / 8); equal half-widths share the X sweep too
+    ctx.set_fast_gauss(True)
+    try:
+        for hw_a, hw_b in ((5, 8), (8, 8), (5, 16)):
+            ga, _ = oracle.apply_gauss(vol, 2.0, hw_a)
+            gb, _ = oracle.apply_gauss(vol, 2.9, hw_b)
+            got, _, _ = ctx.apply_dog(vol, 2.0, 2.9, hw_a, hw_b=hw_b)
+            assert np.abs(got - (ga - gb)).max() <= 8e-7 * np.abs(vol).max(), (hw_a, hw_b)
+    finally:
+        ctx.set_fast_gauss(False)
+
+
 def test_gauss_linearity_and_constant(ctx):
     """size-independent properties at a larger size: linearity; a constant image stays
     constant under the normalised filter (borders included)."""

@@ -304,13 +304,19 @@ class Context:
                                                       _i(int(normalize)), C.byref(A)))
         return dst, A.value
 
-    def apply_dog(self, src, sigma_a, sigma_b, hw, mask=None):
-        """ApplyDog (lib/visfd/filter3d.hpp:1340-1402)."""
+    def apply_dog(self, src, sigma_a, sigma_b, hw, mask=None, hw_b=None):
+        """ApplyDog (lib/visfd/filter3d.hpp:1340-1402); hw_b: the second Gaussian's own half-width, as
+        filter_mrc's -dog gives each Gaussian (bin/filter_mrc/handlers.cpp:HandleDog)."""
         src, mask = _prep(src), _prep(mask)
         dst = _empty(src, src.shape)
         A, B = _f(), _f()
-        self._ck(self.lib.visfd_cuda_apply_dog(self.h, *self._dims(src.shape), _ptr(src), _ptr(dst), _ptr(mask),
-                                               _f3(sigma_a), _f3(sigma_b), _i3(hw), C.byref(A), C.byref(B)))
+        if hw_b is None:
+            self._ck(self.lib.visfd_cuda_apply_dog(self.h, *self._dims(src.shape), _ptr(src), _ptr(dst), _ptr(mask),
+                                                   _f3(sigma_a), _f3(sigma_b), _i3(hw), C.byref(A), C.byref(B)))
+        else:
+            self._ck(self.lib.visfd_cuda_apply_dog2(self.h, *self._dims(src.shape), _ptr(src), _ptr(dst), _ptr(mask),
+                                                    _f3(sigma_a), _f3(sigma_b), _i3(hw), _i3(hw_b), C.byref(A),
+                                                    C.byref(B)))
         return dst, A.value, B.value
 
     def apply_log(self, src, sigma, delta=0.02, truncate_ratio=2.5, mask=None, z_offset=0, nz_global=None):

@@ -428,17 +428,19 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // TMA = true: the tile is fetched by cp.async.bulk.tensor boxes of 8 rows x 128 columns of
 // the 3-D tensor map `tmap` (axis_dim = 1: Y sweep, 2: Z sweep), issued by one thread and
 // tracked by one mbarrier per chunk; TMA = false: per-thread cp.async as described above.
-template <int MODE, bool TMA>
+// DUAL = true: two filters of the same (zero-padded) length over ONE staged tile -- the pair of Gaussians of a
+// DoG / LoG reads the source once: taps_b -> out_b next to taps -> out.
+template <int MODE, bool TMA, bool DUAL>
 __global__ void __launch_bounds__(256, 3)
 sweep_axis3_kernel(const __grid_constant__ CUtensorMap tmap, int axis_dim,
-                   const float *__restrict__ in, float *__restrict__ out,
-                   const float *__restrict__ taps, int hw, int ntap8, int nx, i64 n_axis,
-                   i64 s_axis, i64 s_other) {
+                   const float *__restrict__ in, float *__restrict__ out, float *__restrict__ out_b,
+                   const float *__restrict__ taps, const float *__restrict__ taps_b, int hw, int ntap8, int nx,
+                   i64 n_axis, i64 s_axis, i64 s_other) {
   extern __shared__ __align__(128) float smem[];
   const int rows = ntap8 + A3_NCH * A2_S;      // multiple of 8
   float *tile = smem;                          // [rows][AX_TX]
-  float *tp = smem + (size_t)rows * AX_TX;     // [ntap8]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(tp + ntap8);   // [A3_NCH], TMA only
+  float *tp = smem + (size_t)rows * AX_TX;     // [ntap8] (x 2 if DUAL)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tp + (DUAL ? 2 : 1) * ntap8);   // [A3_NCH], TMA only
   const int lane = threadIdx.x, wy = threadIdx.y;
   const int tid = wy * 32 + lane;
   const int xl = blockIdx.x * AX_TX + 4 * lane;
@@ -484,7 +486,10 @@ sweep_axis3_kernel(const __grid_constant__ CUtensorMap tmap, int axis_dim,
     }
     cp_async_commit_group();
   }
-  if (tid < ntap8) tp[tid] = (tid < 2 * hw + 1) ? taps[tid] : 0.0f;   // ntap8 <= 256 (checked by the host)
+  if (tid < ntap8) {   // ntap8 <= 256 (checked by the host)
+    tp[tid] = (tid < 2 * hw + 1) ? taps[tid] : 0.0f;
+    if (DUAL) tp[ntap8 + tid] = (tid < 2 * hw + 1) ? taps_b[tid] : 0.0f;
+  }
   if (TMA) __syncthreads();   // barriers initialised, taps staged
 
 #pragma unroll 1
@@ -498,6 +503,10 @@ sweep_axis3_kernel(const __grid_constant__ CUtensorMap tmap, int axis_dim,
       else cp_async_wait_group<0>();
       __syncthreads();
     }
+#pragma unroll 1
+    for (int f = 0; f < (DUAL ? 2 : 1); f++) {
+    const float *tpf = tp + f * ntap8;
+    float *outf = f ? out_b : out;
     float2 acc[A2_R][2];
 #pragma unroll
     for (int r = 0; r < A2_R; r++) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
@@ -514,8 +523,8 @@ sweep_axis3_kernel(const __grid_constant__ CUtensorMap tmap, int axis_dim,
     acc[r][1] = tap_acc2<MODE>(acc[r][1], h, make_float2(v.z, v.w));              \
   }
     for (int k0 = 0; k0 < ntap8; k0 += 8) {
-      const float4 ha = *reinterpret_cast<const float4 *>(tp + k0);
-      const float4 hb = *reinterpret_cast<const float4 *>(tp + k0 + 4);
+      const float4 ha = *reinterpret_cast<const float4 *>(tpf + k0);
+      const float4 hb = *reinterpret_cast<const float4 *>(tpf + k0 + 4);
       win[0] = ROW(k0 + 0);
       win[1] = ROW(k0 + 1);
       win[2] = ROW(k0 + 2);
@@ -534,9 +543,10 @@ sweep_axis3_kernel(const __grid_constant__ CUtensorMap tmap, int axis_dim,
       for (int r = 0; r < A2_R; r++) {
         const i64 a = A0 + A2_S * c + A2_R * wy + r;
         if (a < n_axis)
-          *reinterpret_cast<float4 *>(out + base + a * s_axis + xl) =
+          *reinterpret_cast<float4 *>(outf + base + a * s_axis + xl) =
               make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
       }
+    }
     }
   }
 }
@@ -552,6 +562,8 @@ struct XEpilogue {
   // combine: out = (minuend[i] - v) * scale when minuend != NULL (DoG / LoG)
   const float *minuend;
   float scale;
+  // dual X sweep (DoG / LoG): the edge profiles of the second Gaussian; out = (a / den_a - b / den_b) * scale
+  const float *dx_b, *dy_b, *dz_b;
 };
 
 template <int MODE>
@@ -707,11 +719,17 @@ __device__ __forceinline__ void x2_step(float2 (&acc)[XS_RR][2], const float *tb
 
 // EPI: 0 = no normalisation, 1 = divide by the product of the edge profiles, 2 = divide by den3
 // TMA: the two 32-row chunks are boxes (128 + 2 hwpad) x 32 of the 2-D tensor map (x, row).
-template <int MODE, int DELTA, int EPI, bool TMA>
+// DUAL (EPI 1 only): the two chunks are the SAME 32 rows of two inputs (in / tmap with taps, in_b / tmap_b with
+// taps_b, equal half-widths): the last sweep of both Gaussians of a DoG / LoG in one pass.  The first result waits
+// in registers, the second is subtracted from it: neither the first Gaussian nor the "minuend" read of the
+// separate passes ever touches HBM.
+template <int MODE, int DELTA, int EPI, bool TMA, bool DUAL>
 __global__ void __launch_bounds__(256, 3)
-sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ in, float *__restrict__ out,
-                const float *__restrict__ taps, int hw, int nx, i64 nrows, int ny, int nxt,
-                XEpilogue ep) {
+sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
+                const float *__restrict__ in, const float *__restrict__ in_b, float *__restrict__ out,
+                const float *__restrict__ taps, const float *__restrict__ taps_b, int hw, int nx, i64 nrows, int ny,
+                int nxt, XEpilogue ep) {
+  static_assert(!DUAL || EPI == 1, "the dual sweep is the normalised, un-masked DoG");
   extern __shared__ __align__(128) float smem[];
   const int hwpad = (hw + 3) & ~3;
   const int pitch = XS_TX + 2 * hwpad + (TMA ? 0 : 4);
@@ -721,7 +739,8 @@ sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int tid = threadIdx.x;
   const int xt = blockIdx.x % nxt;
-  const i64 row0 = (i64)(blockIdx.x / nxt) * X2_ROWS;
+  const i64 row0 = (i64)(blockIdx.x / nxt) * (DUAL ? 32 : X2_ROWS);
+  const int chunk_rows = DUAL ? 0 : 32;      // first row of chunk c = row0 + chunk_rows * c
   const int x0 = xt * XS_TX;
   const int nvec = (XS_TX + 2 * hwpad) >> 2;
   if (TMA && tid == 0) {
@@ -730,9 +749,10 @@ sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
     mbar_init_fence();
 #pragma unroll
     for (int c = 0; c < 2; c++) {
-      if (row0 + 32 * c >= nrows) break;
+      if (row0 + chunk_rows * c >= nrows) break;
       mbar_expect_tx(bars + c, 32u * (unsigned)pitch * sizeof(float));
-      tma_load_2d(tile + (size_t)32 * c * pitch, &tmap, bars + c, x0 - hwpad, (int)(row0 + 32 * c));
+      tma_load_2d(tile + (size_t)32 * c * pitch, (DUAL && c) ? &tmap_b : &tmap, bars + c, x0 - hwpad,
+                  (int)(row0 + chunk_rows * c));
     }
   }
   // (cp.async) every thread copies a fixed 16-byte column of the tile (two of them for the
@@ -740,17 +760,18 @@ sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
 #pragma unroll
   for (int c = 0; c < 2; c++) {
     if (TMA) break;
-    if (row0 + 32 * c < nrows) {
+    const float *inc = (DUAL && c) ? in_b : in;
+    if (row0 + chunk_rows * c < nrows) {
       for (int cc = lane; cc < nvec; cc += 32) {
         const int x = x0 - hwpad + 4 * cc;
         const bool okx = x >= 0 && x < nx;
-        i64 row = row0 + 32 * c + w;
-        const float *src = okx ? in + row * (i64)nx + x : in;
+        i64 row = row0 + chunk_rows * c + w;
+        const float *src = okx ? inc + row * (i64)nx + x : inc;
         float *dst = tile + (size_t)(32 * c + w) * pitch + 4 * cc;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const bool ok = okx && row < nrows;
-          cp_async16_zfill(dst, ok ? src : in, ok);
+          cp_async16_zfill(dst, ok ? src : inc, ok);
           row += 8;
           src += 8 * (i64)nx;
           dst += 8 * pitch;
@@ -761,28 +782,31 @@ sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
   }
   // taps, placed so that the 8-float window of every step is 16-byte aligned, plus a copy
   // shifted by one float (tp1[k] = tp[k+1]) so that odd tap pairs are aligned pairs too
+  // (DUAL: the same pair of arrays for taps_b behind them)
   const int ntap = 2 * hw + 1;
   const int P = 16 + ((3 - hw - hwpad) & 3);
   const int tplen = (P + ntap + 16 + 3) & ~3;
-  float *tp1 = tp + tplen;
   for (int k = tid; k < tplen; k += 256) {
     const int t = k - P;
     tp[k] = (t >= 0 && t < ntap) ? taps[t] : 0.0f;
-    tp1[k] = (t + 1 >= 0 && t + 1 < ntap) ? taps[t + 1] : 0.0f;
+    tp[tplen + k] = (t + 1 >= 0 && t + 1 < ntap) ? taps[t + 1] : 0.0f;
+    if (DUAL) {
+      tp[2 * tplen + k] = (t >= 0 && t < ntap) ? taps_b[t] : 0.0f;
+      tp[3 * tplen + k] = (t + 1 >= 0 && t + 1 < ntap) ? taps_b[t + 1] : 0.0f;
+    }
   }
   const int nsteps = (2 * hwpad + 4) >> 2;
-  const float *tb0 = tp + P + hw + hwpad - 3;
-  const float *tb1 = tp1 + P + hw + hwpad - 3;
   const int xo = x0 + 4 * lane;
   float dxv[4] = {1.f, 1.f, 1.f, 1.f};
-  if (EPI == 1 && xo < nx) {
+  if (EPI == 1 && !DUAL && xo < nx) {
 #pragma unroll
     for (int e = 0; e < 4; e++) dxv[e] = __ldg(ep.dx + xo + e);
   }
+  float keep[XS_RR][4];   // DUAL: the first Gaussian's rows
 
 #pragma unroll 1
   for (int c = 0; c < 2; c++) {
-    if (row0 + 32 * c >= nrows) break;  // uniform
+    if (row0 + chunk_rows * c >= nrows) break;  // uniform
     if (TMA) {
       if (c == 0) __syncthreads();   // barriers initialised, taps staged
       mbar_wait(bars + c, 0);
@@ -790,6 +814,9 @@ sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
       if (c == 0) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
       __syncthreads();
     }
+    const bool second = DUAL && c == 1;
+    const float *tb0 = tp + (second ? 2 * tplen : 0) + P + hw + hwpad - 3;
+    const float *tb1 = tb0 + tplen;
     float2 acc[XS_RR][2];   // outputs (0,1) and (2,3) of each row
 #pragma unroll
     for (int i = 0; i < XS_RR; i++) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
@@ -803,7 +830,7 @@ sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
       x2_step<MODE, DELTA, 0>(acc, tb0, tb1, trow, pitch, 0);
     }
     if (xo >= nx) continue;
-    const i64 rb = row0 + 32 * c + w * XS_RR;
+    const i64 rb = row0 + chunk_rows * c + w * XS_RR;
     unsigned iz = 0, iy = 0;
     if (EPI == 1) {   // rows < 2^32 (checked by the host)
       iz = (unsigned)rb / (unsigned)ny;
@@ -813,14 +840,19 @@ sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
     float *op = out + o0;
     const float *mp = ep.minuend ? ep.minuend + o0 : nullptr;
     const float *dp = EPI == 2 ? ep.den3 + o0 : nullptr;
+    const float *pdy = second ? ep.dy_b : ep.dy, *pdz = second ? ep.dz_b : ep.dz;
     const int nrow_here = (int)min((i64)XS_RR, nrows - rb);
+    if (DUAL) {   // each Gaussian has its own profile
+#pragma unroll
+      for (int e = 0; e < 4; e++) dxv[e] = __ldg((second ? ep.dx_b : ep.dx) + xo + e);
+    }
 #pragma unroll
     for (int i = 0; i < XS_RR; i++) {
       if (i >= nrow_here) break;
       float r4[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
       if (EPI == 1) {
         while (iy >= (unsigned)ny) { iy -= ny; iz++; }
-        const float dy = __ldg(ep.dy + iy), dz = __ldg(ep.dz + iz);
+        const float dy = __ldg(pdy + iy), dz = __ldg(pdz + iz);
         iy++;
         // filter3d.hpp:1016-1019: den = (dx*dy)*dz, IEEE division.  x / 1 == x, so the
         // interior is skipped whenever the taps sum to exactly 1 (one test per row).
@@ -838,7 +870,15 @@ sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
         if (den.z > 0.0f) r4[2] = __fdiv_rn(r4[2], den.z);
         if (den.w > 0.0f) r4[3] = __fdiv_rn(r4[3], den.w);
       }
-      if (mp) {
+      if (DUAL) {
+        if (c == 0) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) keep[i][e] = r4[e];
+          continue;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) r4[e] = __fmul_rn(__fsub_rn(keep[i][e], r4[e]), ep.scale);
+      } else if (mp) {
         const float4 mn = ld4(mp + (size_t)i * nx);
         r4[0] = __fmul_rn(__fsub_rn(mn.x, r4[0]), ep.scale);
         r4[1] = __fmul_rn(__fsub_rn(mn.y, r4[1]), ep.scale);
@@ -898,16 +938,20 @@ static void launch_axis2_mode(visfd_ctx *ctx, const float *in, float *out, const
   ctx->count_launch();
 }
 
-template <int MODE>
-static bool launch_axis3_mode(visfd_ctx *ctx, const float *in, float *out, const float *d_taps, int hw,
-                              i64 nx, i64 n_axis, i64 s_axis, i64 n_other, i64 s_other) {
+// out_b / d_taps_b != NULL: the dual form (both tap arrays hold 2 hw + 1 entries)
+template <int MODE, bool DUAL>
+static bool launch_axis3_impl(visfd_ctx *ctx, const float *in, float *out, float *out_b, const float *d_taps,
+                              const float *d_taps_b, int hw, i64 nx, i64 n_axis, i64 s_axis, i64 n_other,
+                              i64 s_other) {
   const int ntap8 = (2 * hw + 1 + 7) & ~7;
-  const size_t smem = ((size_t)(ntap8 + A3_NCH * A2_S) * AX_TX + ntap8) * sizeof(float) + A3_NCH * sizeof(uint64_t);
-  const bool vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  const size_t smem = ((size_t)(ntap8 + A3_NCH * A2_S) * AX_TX + (DUAL ? 2 : 1) * ntap8) * sizeof(float) +
+                      A3_NCH * sizeof(uint64_t);
+  const bool vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0) &&
+                      (((uintptr_t)out_b & 15) == 0);
   if (!vec_ok || smem > 100 * 1024 || ntap8 > 256 || n_other > 65535 || div_up(n_axis, A3_NCH * A2_S) > 65535) return false;
   // per launch: the attribute is per DEVICE and a process may hold contexts on several GPUs
-  VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE, true, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  VCK(cudaFuncSetAttribute(sweep_axis3_kernel<MODE, false, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   dim3 grid(div_up(nx, AX_TX), div_up(n_axis, A3_NCH * A2_S), (unsigned)n_other);
   dim3 block(32, 8);
   // the volume as a 3-D tensor (x, y, z): Y sweep: s_axis == nx; Z sweep: s_other == nx
@@ -918,14 +962,21 @@ static bool launch_axis3_mode(visfd_ctx *ctx, const float *in, float *out, const
   memset(&tmap, 0, sizeof(tmap));
   const bool consistent = axis_dim == 1 ? (s_other == nx * n_axis) : (s_axis == nx * n_other);
   if (ctx->use_tma && consistent && make_tensor_map(&tmap, in, 3, dims, box))
-    sweep_axis3_kernel<MODE, true><<<grid, block, smem, ctx->stream>>>(tmap, axis_dim, in, out, d_taps, hw, ntap8,
-                                                                      (int)nx, n_axis, s_axis, s_other);
+    sweep_axis3_kernel<MODE, true, DUAL><<<grid, block, smem, ctx->stream>>>(
+        tmap, axis_dim, in, out, out_b, d_taps, d_taps_b, hw, ntap8, (int)nx, n_axis, s_axis, s_other);
   else
-    sweep_axis3_kernel<MODE, false><<<grid, block, smem, ctx->stream>>>(tmap, axis_dim, in, out, d_taps, hw, ntap8,
-                                                                       (int)nx, n_axis, s_axis, s_other);
+    sweep_axis3_kernel<MODE, false, DUAL><<<grid, block, smem, ctx->stream>>>(
+        tmap, axis_dim, in, out, out_b, d_taps, d_taps_b, hw, ntap8, (int)nx, n_axis, s_axis, s_other);
   VCK(cudaGetLastError());
   ctx->count_launch();
   return true;
+}
+
+template <int MODE>
+static bool launch_axis3_mode(visfd_ctx *ctx, const float *in, float *out, const float *d_taps, int hw,
+                              i64 nx, i64 n_axis, i64 s_axis, i64 n_other, i64 s_other) {
+  return launch_axis3_impl<MODE, false>(ctx, in, out, nullptr, d_taps, nullptr, hw, nx, n_axis, s_axis, n_other,
+                                        s_other);
 }
 
 static void launch_axis(visfd_ctx *ctx, const float *in, float *out, const float *mask,
@@ -947,8 +998,76 @@ static void launch_axis(visfd_ctx *ctx, const float *in, float *out, const float
     launch_axis_mode<MODE_EXACT>(ctx, in, out, mask, d_taps, hw, nx, n_axis, s_axis, n_other, s_other);
 }
 
+static size_t x2_smem_bytes(bool dual, int hw) {
+  const int hwpad = (hw + 3) & ~3;
+  const int pitch = XS_TX + 2 * hwpad + 4;
+  return ((size_t)X2_ROWS * pitch + 8 + (dual ? 4 : 2) * (2 * hw + 1 + 40)) * sizeof(float);
+}
+static bool x2_qualifies(bool dual, i64 nx, i64 nrows, int hw) {
+  const i64 nxt = div_up(nx, XS_TX), nrt = div_up(nrows, (i64)(dual ? 32 : X2_ROWS));
+  return nx % 4 == 0 && x2_smem_bytes(dual, hw) <= 100 * 1024 && nxt * nrt <= 2147483647LL && nrows < 4294967296LL;
+}
+
+// The pipelined X sweep; in_b / d_taps_b != NULL: its dual form (DoG / LoG, see the kernel).  Returns false when the
+// volume does not qualify (nothing launched).
+static bool launch_x2(visfd_ctx *ctx, const float *in, const float *in_b, float *out, const float *d_taps,
+                      const float *d_taps_b, int hw, i64 nx, i64 ny, i64 nrows, const XEpilogue &ep) {
+  const bool dual = in_b != nullptr;
+  const int hwpad = (hw + 3) & ~3;
+  const bool vec_ok = (((uintptr_t)in & 15) == 0) && (((uintptr_t)in_b & 15) == 0) &&
+                      (((uintptr_t)out & 15) == 0) && (!ep.den3 || ((uintptr_t)ep.den3 & 15) == 0) &&
+                      (!ep.minuend || ((uintptr_t)ep.minuend & 15) == 0);
+  if (!vec_ok || !x2_qualifies(dual, nx, nrows, hw)) return false;
+  const size_t smem2 = x2_smem_bytes(dual, hw);
+  const i64 nxt = div_up(nx, XS_TX), nrt = div_up(nrows, (i64)(dual ? 32 : X2_ROWS));
+  if (dual && !(ep.dx && ep.dx_b && !ep.den3 && !ep.minuend)) return false;
+  CUtensorMap tmap, tmap_b;
+  memset(&tmap, 0, sizeof(tmap));
+  memset(&tmap_b, 0, sizeof(tmap_b));
+  const i64 dims2[2] = {nx, nrows};
+  const int box2[2] = {XS_TX + 2 * hwpad, 32};
+  const bool tma = ctx->use_tma && make_tensor_map(&tmap, in, 2, dims2, box2) &&
+                   (!dual || make_tensor_map(&tmap_b, in_b, 2, dims2, box2));
+  const unsigned grid = (unsigned)(nxt * nrt);   // 1-D grid, x tiles fastest
+  // (the attribute is set per launch: it is per DEVICE and a process may hold contexts on several GPUs)
+#define X2_LAUNCH_T(M, D, E, T, U)                                                                                \
+  do {                                                                                                            \
+    VCK(cudaFuncSetAttribute(sweep_x2_kernel<M, D, E, T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+    sweep_x2_kernel<M, D, E, T, U><<<grid, 256, smem2, ctx->stream>>>(tmap, tmap_b, in, in_b, out, d_taps, d_taps_b, hw, \
+                                                                      (int)nx, nrows, (int)ny, (int)nxt, ep);     \
+  } while (0)
+#define X2_LAUNCH_E(M, D, E, U)                          \
+  do {                                                   \
+    if (tma) X2_LAUNCH_T(M, D, E, true, U);              \
+    else X2_LAUNCH_T(M, D, E, false, U);                 \
+  } while (0)
+#define X2_LAUNCH(M, D)                                  \
+  do {                                                   \
+    if (dual) X2_LAUNCH_E(M, D, 1, true);                \
+    else if (ep.dx) X2_LAUNCH_E(M, D, 1, false);         \
+    else if (ep.den3) X2_LAUNCH_E(M, D, 2, false);       \
+    else X2_LAUNCH_E(M, D, 0, false);                    \
+  } while (0)
+#define X2_LAUNCH_D(M)                                   \
+  switch (hwpad - hw) {                                  \
+    case 0: X2_LAUNCH(M, 0); break;                      \
+    case 1: X2_LAUNCH(M, 1); break;                      \
+    case 2: X2_LAUNCH(M, 2); break;                      \
+    default: X2_LAUNCH(M, 3); break;                     \
+  }
+  if (ctx->fast_gauss) { X2_LAUNCH_D(MODE_FAST) } else { X2_LAUNCH_D(MODE_EXACT) }
+#undef X2_LAUNCH_D
+#undef X2_LAUNCH
+#undef X2_LAUNCH_E
+#undef X2_LAUNCH_T
+  VCK(cudaGetLastError());
+  ctx->count_launch();
+  return true;
+}
+
 static void launch_x(visfd_ctx *ctx, const float *in, float *out, const float *d_taps, int hw,
                      i64 nx, i64 ny, i64 nrows, const XEpilogue &ep) {
+  if (launch_x2(ctx, in, nullptr, out, d_taps, nullptr, hw, nx, ny, nrows, ep)) return;
   const int hwpad = (hw + 3) & ~3;
   const int pitch = XS_TX + 2 * hwpad + 4;
   size_t smem = ((size_t)XS_ROWS * pitch + (2 * hw + 1 + TAP_PAD_LO + TAP_PAD_HI)) * sizeof(float);
@@ -958,46 +1077,6 @@ static void launch_x(visfd_ctx *ctx, const float *in, float *out, const float *d
   VCK(cudaFuncSetAttribute(sweep_x_kernel<MODE_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   int vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0) &&
                (!ep.den3 || ((uintptr_t)ep.den3 & 15) == 0) && (!ep.minuend || ((uintptr_t)ep.minuend & 15) == 0);
-  {
-    // pipelined kernel: 1-D grid, x tiles fastest
-    const size_t smem2 = ((size_t)X2_ROWS * pitch + 8 + 2 * (2 * hw + 1 + 40)) * sizeof(float);
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    const i64 dims2[2] = {nx, nrows};
-    const int box2[2] = {XS_TX + 2 * hwpad, 32};
-    const bool tma = ctx->use_tma && make_tensor_map(&tmap, in, 2, dims2, box2);
-    const i64 nxt = div_up(nx, XS_TX), nrt = (nrows + X2_ROWS - 1) / X2_ROWS;
-    if (vec_ok && smem2 <= 100 * 1024 && nxt * nrt <= 2147483647LL && nrows < 4294967296LL) {
-      const unsigned grid = (unsigned)(nxt * nrt);
-#define X2_LAUNCH_E(M, D, E)                                                                                  \
-      do {                                                                                                    \
-        VCK(cudaFuncSetAttribute(sweep_x2_kernel<M, D, E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
-        VCK(cudaFuncSetAttribute(sweep_x2_kernel<M, D, E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
-        if (tma) sweep_x2_kernel<M, D, E, true><<<grid, 256, smem2, ctx->stream>>>(tmap, in, out, d_taps, hw, (int)nx, nrows, (int)ny, (int)nxt, ep); \
-        else sweep_x2_kernel<M, D, E, false><<<grid, 256, smem2, ctx->stream>>>(tmap, in, out, d_taps, hw, (int)nx, nrows, (int)ny, (int)nxt, ep); \
-      } while (0)
-#define X2_LAUNCH(M, D)                                  \
-      do {                                               \
-        if (ep.dx) X2_LAUNCH_E(M, D, 1);                 \
-        else if (ep.den3) X2_LAUNCH_E(M, D, 2);          \
-        else X2_LAUNCH_E(M, D, 0);                       \
-      } while (0)
-#define X2_LAUNCH_D(M)                                   \
-      switch (hwpad - hw) {                              \
-        case 0: X2_LAUNCH(M, 0); break;                  \
-        case 1: X2_LAUNCH(M, 1); break;                  \
-        case 2: X2_LAUNCH(M, 2); break;                  \
-        default: X2_LAUNCH(M, 3); break;                 \
-      }
-      if (ctx->fast_gauss) { X2_LAUNCH_D(MODE_FAST) } else { X2_LAUNCH_D(MODE_EXACT) }
-#undef X2_LAUNCH_D
-#undef X2_LAUNCH
-#undef X2_LAUNCH_E
-      VCK(cudaGetLastError());
-      ctx->count_launch();
-      return;
-    }
-  }
   // rows go on grid.x (2^31-1 blocks), x tiles on grid.y
   i64 gx = (nrows + XS_ROWS - 1) / XS_ROWS;
   VREQUIRE(gx <= 2147483647LL && div_up(nx, XS_TX) <= 65535, "volume too large for one launch");
@@ -1023,7 +1102,7 @@ void fill_device(visfd_ctx *ctx, float *p, float v, i64 n) {
 float separable_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
                        const float *src, float *dst, const float *mask, const float *const taps[3],
                        const int hw[3], bool normalize, const float *combine_minuend,
-                       float combine_scale) {
+                       float combine_scale, bool z_swept) {
   StageTimer timer(ctx, "gauss");
   const i64 N = nx * ny * nz_local;
   VREQUIRE(nx > 0 && ny > 0 && nz_local > 0, "empty volume");
@@ -1031,8 +1110,10 @@ float separable_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offse
   VREQUIRE(z_offset >= 0 && z_offset + nz_local <= nz_global, "slab outside the volume");
   // The Z sweep reads src while other CTAs already write dst: unlike the reference (one temporary per line,
   // filter3d.hpp:710-713 copies first) the device path cannot filter in place
-  VREQUIRE(src != dst && (!mask || mask != dst) && (!combine_minuend || combine_minuend != dst),
+  // (z_swept: dst already holds the Z sweep of the source -- dog_device's shared sweep -- and src is not read)
+  VREQUIRE((z_swept || src != dst) && (!mask || mask != dst) && (!combine_minuend || combine_minuend != dst),
            "separable filter: dst must not alias src, mask or the minuend (device pointers)");
+  VREQUIRE(!z_swept || !mask, "separable filter: the shared Z sweep has no masked form");
   // upload taps (+ edge profiles) in one host buffer
   const int nt[3] = {2 * hw[0] + 1, 2 * hw[1] + 1, 2 * hw[2] + 1};
   const i64 n_dim[3] = {nx, ny, nz_local};
@@ -1059,7 +1140,7 @@ float separable_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offse
   ep.scale = combine_scale;
   if (!mask) {
     // Z: src -> dst ; Y: dst -> tmp ; X: tmp -> dst
-    launch_axis(ctx, src, dst, nullptr, tz, hw[2], nx, nz_local, nx * ny, ny, nx);
+    if (!z_swept) launch_axis(ctx, src, dst, nullptr, tz, hw[2], nx, nz_local, nx * ny, ny, nx);
     launch_axis(ctx, dst, tmp.get(), nullptr, ty, hw[1], nx, ny, nx, nz_local, nx * ny);
     if (plain_norm) {
       ep.dx = dconst.get() + off_d[0];
@@ -1089,7 +1170,8 @@ float separable_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offse
 
 float gauss_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
                    const float *src, float *dst, const float *mask, const float sigma[3],
-                   const int hw[3], bool normalize, const float *combine_minuend, float combine_scale) {
+                   const int hw[3], bool normalize, const float *combine_minuend, float combine_scale,
+                   bool z_swept) {
   std::vector<float> t[3];
   const float *tp[3];
   for (int d = 0; d < 3; d++) {
@@ -1099,7 +1181,33 @@ float gauss_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i
     tp[d] = t[d].data();
   }
   return separable_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, dst, mask, tp, hw,
-                          normalize, combine_minuend, combine_scale);
+                          normalize, combine_minuend, combine_scale, z_swept);
+}
+
+// The Z sweeps of two Gaussians over one read of the source: src -> (dst_a, dst_b).  Both tap arrays are centred in
+// 2 hw + 1 entries, hw = the larger half-width; the padding taps are zeros, which add +-0 to the running sums in
+// the same order as before and so leave every finite result bit for bit what the separate sweeps give.
+// Returns false (nothing launched) when the pair does not qualify.
+static bool dual_z_sweep(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, const float *src, float *dst_a, float *dst_b,
+                         float sigma_a, int hw_a, float sigma_b, int hw_b) {
+  const int hw = std::max(hw_a, hw_b);
+  // padding the shorter filter costs arithmetic: measured on B200, one extra group of 8 taps still pays with FMA
+  // accumulation (DoG sigma 2 / 3.2: 1.34 -> 1.29 ms at 512^3) and does not in the bit-exact mode (1.63 -> 1.67)
+  const int extra = ((2 * hw + 8) & ~7) - ((2 * std::min(hw_a, hw_b) + 8) & ~7);
+  if (extra > (ctx->fast_gauss ? 8 : 0)) return false;
+  if (src == dst_a || src == dst_b || dst_a == dst_b) return false;
+  const int nt = 2 * hw + 1;
+  std::vector<float> h(2 * (size_t)nt, 0.0f);
+  gen_gauss1d(sigma_a, hw_a, h.data() + (hw - hw_a));
+  gen_gauss1d(sigma_b, hw_b, h.data() + nt + (hw - hw_b));
+  Scratch<float> d(ctx, 2 * (size_t)nt);
+  VCK(cudaMemcpyAsync(d.get(), h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  StageTimer timer(ctx, "gauss");
+  return ctx->fast_gauss
+             ? launch_axis3_impl<MODE_FAST, true>(ctx, src, dst_a, dst_b, d.get(), d.get() + nt, hw, nx, nz_local,
+                                                  nx * ny, ny, nx)
+             : launch_axis3_impl<MODE_EXACT, true>(ctx, src, dst_a, dst_b, d.get(), d.get() + nt, hw, nx, nz_local,
+                                                   nx * ny, ny, nx);
 }
 
 // ApplyDog (filter3d.hpp:1340-1402): dst = G_a(src) - G_b(src), optionally * scale (ApplyLog).
@@ -1108,10 +1216,71 @@ void dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 
                 const float sigma_b[3], const int hw[3], float scale, float *A, float *B, const int *hw_b) {
   const i64 N = nx * ny * nz_local;
   Scratch<float> ga(ctx, N);
+  const int *hb = hw_b ? hw_b : hw;
+  for (int d = 0; d < 3; d++)
+    VREQUIRE(hw[d] >= 0 && hb[d] >= 0 && sigma_a[d] >= 0.0f && sigma_b[d] >= 0.0f, "negative sigma or half-width");
+  if (!mask && hw[0] == hb[0] && hw[1] == hb[1] && hw[2] == hb[2] && ((uintptr_t)dst & 15) == 0 && src != dst &&
+      x2_qualifies(true, nx, ny * nz_local, hw[0])) {
+    // Both Gaussians in four launches and 40 B / voxel instead of six and 52 (ApplyLog's pair always has equal
+    // half-widths, filter3d.hpp:1460-1464): one Z sweep of the source for both, a Y sweep each, one X sweep that
+    // normalises both, subtracts and scales.  Same operations on the same values in the same order as the two
+    // separate filters: bit-identical to them.
+    StageTimer timer(ctx, "gauss");
+    VREQUIRE(nx > 0 && ny > 0 && nz_local > 0, "empty volume");
+    VREQUIRE(z_offset >= 0 && z_offset + nz_local <= nz_global, "slab outside the volume");
+    const int nt[3] = {2 * hw[0] + 1, 2 * hw[1] + 1, 2 * hw[2] + 1};
+    const i64 n_dim[3] = {nx, ny, nz_local};
+    const size_t per = (size_t)nt[0] + nt[1] + nt[2] + nx + ny + nz_local;
+    std::vector<float> h(2 * per);
+    size_t off_t[3], off_d[3], o = 0;
+    for (int d = 0; d < 3; d++) { off_t[d] = o; o += nt[d]; }
+    for (int d = 0; d < 3; d++) { off_d[d] = o; o += n_dim[d]; }
+    float centre[2] = {1.0f, 1.0f};
+    for (int f = 0; f < 2; f++) {
+      float *hf = h.data() + f * per;
+      const float *sg = f ? sigma_b : sigma_a;
+      for (int d = 0; d < 3; d++) {
+        gen_gauss1d(sg[d], hw[d], hf + off_t[d]);
+        centre[f] *= hf[off_t[d] + hw[d]];   // filter3d.hpp:1044-1046
+      }
+      edge_profile(hf + off_t[0], hw[0], nx, 0, nx, hf + off_d[0]);
+      edge_profile(hf + off_t[1], hw[1], ny, 0, ny, hf + off_d[1]);
+      edge_profile(hf + off_t[2], hw[2], nz_global, z_offset, nz_local, hf + off_d[2]);
+    }
+    Scratch<float> dconst(ctx, 2 * per), tmp(ctx, N);
+    VCK(cudaMemcpyAsync(dconst.get(), h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    const float *ca = dconst.get(), *cb = dconst.get() + per;
+    // Z: src -> (ga, dst)
+    const bool z_dual =
+        ctx->fast_gauss ? launch_axis3_impl<MODE_FAST, true>(ctx, src, ga.get(), dst, ca + off_t[2], cb + off_t[2], hw[2],
+                                                             nx, nz_local, nx * ny, ny, nx)
+                        : launch_axis3_impl<MODE_EXACT, true>(ctx, src, ga.get(), dst, ca + off_t[2], cb + off_t[2], hw[2],
+                                                              nx, nz_local, nx * ny, ny, nx);
+    if (!z_dual) {
+      launch_axis(ctx, src, ga.get(), nullptr, ca + off_t[2], hw[2], nx, nz_local, nx * ny, ny, nx);
+      launch_axis(ctx, src, dst, nullptr, cb + off_t[2], hw[2], nx, nz_local, nx * ny, ny, nx);
+    }
+    // Y: ga -> tmp, dst -> ga
+    launch_axis(ctx, ga.get(), tmp.get(), nullptr, ca + off_t[1], hw[1], nx, ny, nx, nz_local, nx * ny);
+    launch_axis(ctx, dst, ga.get(), nullptr, cb + off_t[1], hw[1], nx, ny, nx, nz_local, nx * ny);
+    // X: (tmp, ga) -> dst
+    XEpilogue ep{};
+    ep.scale = scale;
+    ep.dx = ca + off_d[0]; ep.dy = ca + off_d[1]; ep.dz = ca + off_d[2];
+    ep.dx_b = cb + off_d[0]; ep.dy_b = cb + off_d[1]; ep.dz_b = cb + off_d[2];
+    const bool x_dual = launch_x2(ctx, tmp.get(), ga.get(), dst, ca + off_t[0], cb + off_t[0], hw[0], nx, ny,
+                                  ny * nz_local, ep);
+    VREQUIRE(x_dual, "dog: the shared X sweep did not launch");   // x2_qualifies() said it would
+    if (A) *A = centre[0];
+    if (B) *B = centre[1];
+    return;
+  }
+  const bool z_swept = !mask && dual_z_sweep(ctx, nx, ny, nz_local, src, ga.get(), dst, sigma_a[2], hw[2],
+                                             sigma_b[2], hb[2]);
   float a = gauss_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, ga.get(), mask, sigma_a, hw,
-                         true, nullptr, 1.0f);
-  float b = gauss_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, dst, mask, sigma_b, hw_b ? hw_b : hw, true,
-                         ga.get(), scale);
+                         true, nullptr, 1.0f, z_swept);
+  float b = gauss_device(ctx, nx, ny, nz_local, z_offset, nz_global, src, dst, mask, sigma_b, hb, true,
+                         ga.get(), scale, z_swept);
   if (A) *A = a;
   if (B) *B = b;
 }

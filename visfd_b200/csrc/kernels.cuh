@@ -11,11 +11,11 @@ void gen_gauss1d(float sigma, int hw, float *taps);
 float separable_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
                        const float *src, float *dst, const float *mask, const float *const taps[3],
                        const int hw[3], bool normalize, const float *combine_minuend,
-                       float combine_scale);
+                       float combine_scale, bool z_swept = false /* dst already holds the Z sweep (dog_device) */);
 float gauss_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
                    const float *src, float *dst, const float *mask, const float sigma[3],
                    const int hw[3], bool normalize, const float *combine_minuend,
-                   float combine_scale);
+                   float combine_scale, bool z_swept = false);
 void dog_device(visfd_ctx *ctx, i64 nx, i64 ny, i64 nz_local, i64 z_offset, i64 nz_global,
                 const float *src, float *dst, const float *mask, const float sigma_a[3],
                 const float sigma_b[3], const int hw[3], float scale, float *A, float *B,
