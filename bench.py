@@ -641,7 +641,8 @@ def main():
     fp32_peak_3op = ctx.fp32_peak(300.0, three_operand=True)
     tv_ms = stage["tv"]
     achieved = 35.0 * pairs / (tv_ms * 1e-3) / 1e12
-    roofline = {"kernel": "tv_gather_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
+    tv_kernel_name = "tv_gather_lut_kernel" if ctx.last_tv_kernel() else "tv_gather_kernel"
+    roofline = {"kernel": tv_kernel_name, "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
                 "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                 "traffic": NCU_TRAFFIC_BYTES.get(name) if world == 1 else None,
                 "peak_source": "measured in this run: register-resident FFMA chains (visfd_cuda_fp32_peak); "

@@ -176,8 +176,8 @@ __device__ __forceinline__ float tap_acc(float acc, float h, float v) {
 // Packed FP32 (FMUL2 / FADD2 / FFMA2, each lane-wise IEEE round-to-nearest like the scalar
 // forms, so EXACT stays bit-exact): half the issue slots for the same arithmetic.
 // (ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- unlike the scalar .rn
-// forms, and whatever -fmad says -- so EXACT uses a packed product and two scalar sums:
-// three instructions per two taps instead of four.)
+// forms, and whatever -fmad says -- so EXACT cannot write the sum as a packed add; see
+// mul_then_add2 for the form it uses: two instructions per two taps instead of four.)
 __device__ __forceinline__ unsigned long long f2_bits(float2 v) {
   unsigned long long r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
@@ -188,11 +188,16 @@ __device__ __forceinline__ float2 bits_f2(unsigned long long b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(b));
   return v;
 }
+// The sum: a packed FMA of the ROUNDED product with a multiplier of one -- fma(p, 1, acc) rounds p + acc once,
+// which is the rounded addition.  The one comes from constant memory, so ptxas can neither fold it away nor
+// contract anything: two issue slots per pair of taps (FMUL2 + FFMA2) instead of three (FMUL2 + 2 FADD).
+__constant__ float c_one = 1.0f;
 __device__ __forceinline__ float2 mul_then_add2(float2 acc, float2 a, float2 b) {
-  unsigned long long p;
+  unsigned long long p, r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-  const float2 pr = bits_f2(p);
-  return make_float2(__fadd_rn(acc.x, pr.x), __fadd_rn(acc.y, pr.y));
+  const float one = c_one;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p), "l"(f2_bits(make_float2(one, one))), "l"(f2_bits(acc)));
+  return bits_f2(r);
 }
 template <int MODE>
 __device__ __forceinline__ float2 tap_acc2(float2 acc, float h, float2 v) {
@@ -522,7 +527,9 @@ sweep_axis3_kernel(const __grid_constant__ CUtensorMap tmap, int axis_dim,
     acc[r][0] = tap_acc2<MODE>(acc[r][0], h, make_float2(v.x, v.y));              \
     acc[r][1] = tap_acc2<MODE>(acc[r][1], h, make_float2(v.z, v.w));              \
   }
-    for (int k0 = 0; k0 < ntap8; k0 += 8) {
+    const int ntap = 2 * hw + 1;
+    int k0 = 0;
+    for (; k0 + 8 <= ntap; k0 += 8) {
       const float4 ha = *reinterpret_cast<const float4 *>(tpf + k0);
       const float4 hb = *reinterpret_cast<const float4 *>(tpf + k0 + 4);
       win[0] = ROW(k0 + 0);
@@ -535,6 +542,30 @@ sweep_axis3_kernel(const __grid_constant__ CUtensorMap tmap, int axis_dim,
       win[6] = ROW(k0 + 6);
       win[7] = ROW(k0 + 7);
       TAP4(hb.x, 0, 4) TAP4(hb.y, 1, 4) TAP4(hb.z, 2, 4) TAP4(hb.w, 3, 4)
+    }
+    {
+      // the last 1, 3, 5 or 7 taps (the count is odd): the taps that pad the group to 8 are zeros and add
+      // nothing, so they are not evaluated (FP32-pipe time at sigma >= 4)
+      const int rem = ntap - k0;
+      const float4 ha = *reinterpret_cast<const float4 *>(tpf + k0);
+      const float4 hb = *reinterpret_cast<const float4 *>(tpf + k0 + 4);
+      win[0] = ROW(k0 + 0);
+      TAP4(ha.x, 0, 0)
+      if (rem >= 3) {
+        win[1] = ROW(k0 + 1);
+        win[2] = ROW(k0 + 2);
+        TAP4(ha.y, 1, 0) TAP4(ha.z, 2, 0)
+      }
+      if (rem >= 5) {
+        win[3] = ROW(k0 + 3);
+        win[4] = ROW(k0 + 4);
+        TAP4(ha.w, 3, 0) TAP4(hb.x, 0, 4)
+      }
+      if (rem >= 7) {
+        win[5] = ROW(k0 + 5);
+        win[6] = ROW(k0 + 6);
+        TAP4(hb.y, 1, 4) TAP4(hb.z, 2, 4)
+      }
     }
 #undef TAP4
 #undef ROW
