@@ -89,6 +89,12 @@ def test_gauss_fast_mode_tolerance(ctx, oracle):
             got, _ = ctx.apply_gauss(vol, sigma, hw)
             assert rel_err(got, want, floor_frac=1e-2) <= TOL_GAUSS
             assert np.abs(got - want).max() <= 4e-7 * np.abs(want).max()
+        # several CTAs per column, ragged ends
+        vol = synth.tomogram((150, 139, 64), seed=22)
+        for sigma, hw in ((3.0, 8), (5.0, 15), (8.0, 21)):
+            want, _ = oracle.apply_gauss(vol, sigma, hw)
+            got, _ = ctx.apply_gauss(vol, sigma, hw)
+            assert np.abs(got - want).max() <= 4e-7 * np.abs(want).max(), (sigma, hw)
     finally:
         ctx.set_fast_gauss(False)
 

@@ -755,7 +755,7 @@ __device__ __forceinline__ void x2_step(float2 (&acc)[XS_RR][2], const float *tb
 // in registers, the second is subtracted from it: neither the first Gaussian nor the "minuend" read of the
 // separate passes ever touches HBM.
 template <int MODE, int DELTA, int EPI, bool TMA, bool DUAL>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, (DUAL && !TMA) ? 2 : 3)   // (the cp.async fall-back of the dual form needs 4 more registers)
 sweep_x2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
                 const float *__restrict__ in, const float *__restrict__ in_b, float *__restrict__ out,
                 const float *__restrict__ taps, const float *__restrict__ taps_b, int hw, int nx, i64 nrows, int ny,
