@@ -156,6 +156,39 @@ def test_dog_shared_z_sweep_with_unequal_halfwidths(ctx, oracle):
         ctx.set_fast_gauss(False)
 
 
+def test_separable_filters_seeded_sweep_of_shapes(ctx, oracle):
+    """120 seeded cases over ragged and degenerate shapes (one plane, one row, nx not a multiple of 4, several CTAs
+    per column), widths and half-widths (0 included): ApplyGauss, ApplyDog with equal and with unequal half-widths,
+    ApplyLog -- each bit for bit the oracle's."""
+    rng = np.random.default_rng(2024)
+    for it in range(120):
+        nx = int(rng.choice([4, 8, 12, 20, 64, 132, 260, 7, 33]))
+        ny = int(rng.choice([1, 2, 3, 5, 33, 70, 130]))
+        nz = int(rng.choice([1, 2, 7, 40, 100, 140]))
+        vol = rng.standard_normal((nz, ny, nx)).astype(np.float32)
+        sa = float(rng.uniform(0.5, 6.0))
+        sb = sa * float(rng.uniform(1.01, 1.8))
+        ratio = float(rng.uniform(1.5, 3.0))
+        hw = max(1, int(ratio * sb)) if rng.random() < 0.9 else 0
+        kind = ("gauss", "dog", "dog2", "log")[int(rng.integers(0, 4))]
+        if kind == "gauss":
+            want, _ = oracle.apply_gauss(vol, sa, hw)
+            got, _ = ctx.apply_gauss(vol, sa, hw)
+        elif kind == "dog":
+            want, _, _ = oracle.apply_dog(vol, sa, sb, hw)
+            got, _, _ = ctx.apply_dog(vol, sa, sb, hw)
+        elif kind == "dog2":
+            hwa = max(0, hw - int(rng.integers(0, 6)))
+            ga, _ = oracle.apply_gauss(vol, sa, hwa)
+            gb, _ = oracle.apply_gauss(vol, sb, hw)
+            want = ga - gb
+            got, _, _ = ctx.apply_dog(vol, sa, sb, hwa, hw_b=hw)
+        else:
+            want, _, _ = oracle.apply_log(vol, sa, 0.02, ratio)
+            got, _, _ = ctx.apply_log(vol, sa, 0.02, ratio)
+        assert np.array_equal(got, want), (it, kind, vol.shape, sa, sb, hw)
+
+
 def test_gauss_linearity_and_constant(ctx):
     """size-independent properties at a larger size: linearity; a constant image stays
     constant under the normalised filter (borders included)."""
